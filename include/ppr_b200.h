@@ -1,0 +1,134 @@
+/* ppr_b200.h -- C ABI of the B200-native rollout path (libppr_b200.so).
+ *
+ * Drop-in boundary for the two torch.autograd Functions of the reference
+ *   ForwardKinematics   /root/reference/diffphys/dp_model.py:1022-1130
+ *   ForwardWarp         /root/reference/diffphys/dp_model.py:1145-1400
+ * which in the reference drive Warp kernels (diffphys/integrator_euler.py:21-620 and warp.sim.eval_fk) under a
+ * wp.Tape.  Everything here takes plain device pointers + sizes + a cudaStream_t (as void*); no torch types.
+ *
+ * Conventions (the reference's): fp32; quaternions xyzw; transform = (p[3], q[4]); spatial vectors =
+ * (angular[3], linear[3]); env e owns bodies [e*nb,(e+1)*nb), coords [e*nq,(e+1)*nq), dofs [e*nqd,(e+1)*nqd)
+ * (dp_model.py:563-572,697-699).
+ *
+ * Error convention: every function returns int: 0 ok, <0 argument / shape error (PPR_E_*), >0 a cudaError_t.
+ * Nothing throws, nothing synchronises the device, no thread-local state: re-entrant from the autograd thread.
+ */
+#ifndef PPR_B200_H
+#define PPR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPR_E_ARG (-1)      /* null / inconsistent argument */
+#define PPR_E_SHAPE (-2)    /* unsupported size (nb > 32, dofs per joint > 3, ...) */
+#define PPR_E_HANDLE (-3)   /* bad model handle */
+#define PPR_E_WORKSPACE (-4)/* workspace too small */
+
+/* Static arrays of ONE articulation -- what the reference's kernels read from the Warp `Model`
+ * (integrator_euler.py:497-504, 519-538, 603-611).  HOST pointers; copied at create time. */
+typedef struct ppr_model_desc {
+    int32_t nb, nq, nqd, nc, nshape;
+    const int32_t* joint_type;      /* [nb]  Warp enum: 1 REVOLUTE, 3 FIXED, 4 FREE, 5 COMPOUND */
+    const int32_t* joint_parent;    /* [nb]  -1 = world; parents precede children */
+    const int32_t* joint_q_start;   /* [nb] */
+    const int32_t* joint_qd_start;  /* [nb] */
+    const float* joint_X_p;         /* [nb,7] */
+    const float* joint_X_c;         /* [nb,7] */
+    const float* joint_axis;        /* [nb,3] */
+    const float* joint_limit_lower; /* [nqd] */
+    const float* joint_limit_upper; /* [nqd] */
+    const float* joint_limit_ke;    /* [nqd] */
+    const float* joint_limit_kd;    /* [nqd] */
+    const float* body_com;          /* [nb,3] */
+    const int32_t* contact_body;    /* [nc] */
+    const float* contact_point;     /* [nc,3] body frame */
+    const float* contact_dist;      /* [nc] */
+    const int32_t* contact_material;/* [nc] row of shape_materials */
+    const float* shape_materials;   /* [nshape,4] ke kd kf mu */
+    float gravity[3];
+    float joint_attach_ke, joint_attach_kd;
+} ppr_model_desc;
+
+typedef struct ppr_model* ppr_model_t;
+
+const char* ppr_version(void);
+
+/* Uploads one copy of the static arrays to the current CUDA device (reference: ModelBuilder.finalize +
+ * Model.collide, dp_model.py:384-401, which replicate them num_envs times). */
+int ppr_model_create(const ppr_model_desc* desc, ppr_model_t* out);
+int ppr_model_destroy(ppr_model_t m);
+/* lab4d overwrites env.joint_X_p from torch every step (diffphys/dp_interface.py:465): HOST pointer, [nb,7]. */
+int ppr_model_set_joint_X_p(ppr_model_t m, const float* joint_X_p, void* stream);
+int ppr_model_set_attach(ppr_model_t m, float attach_ke, float attach_kd);
+int ppr_model_set_gravity(ppr_model_t m, const float g[3]);
+/* introspection: environments packed per warp, lanes used per warp */
+int ppr_model_envs_per_warp(ppr_model_t m);
+
+/* ---- articulation FK (replaces eval_fk launches at dp_model.py:1068 and its tape adjoint :1101) ------------
+ * n = number of independent articulations (reference: T frames x bs envs, one launch per frame).
+ * joint_q [n,nq], joint_qd [n,nqd] -> body_q [n,nb,7], body_qd [n,nb,6]. */
+int ppr_fk_forward(ppr_model_t m, int64_t n, const float* joint_q, const float* joint_qd, float* body_q,
+                   float* body_qd, void* stream);
+/* adj_joint_q [n,nq], adj_joint_qd [n,nqd] are OVERWRITTEN. */
+int ppr_fk_backward(ppr_model_t m, int64_t n, const float* joint_q, const float* joint_qd, const float* adj_body_q,
+                    const float* adj_body_qd, float* adj_joint_q, float* adj_joint_qd, void* stream);
+
+/* ---- rollout (replaces ForwardWarp.forward / .backward, dp_model.py:1147-1400) ----------------------------
+ * nsteps = T substeps simulated (reference: len(steps_idx) = spf*(F-1)+1, dp_model.py:357-359);
+ * frame_stride = spf; nframes = F outputs at t = k*frame_stride (t < nsteps).
+ * The state saved for the adjoint lives in `workspace` (ppr_rollout_workspace_bytes); the same buffer must be
+ * handed to ppr_rollout_backward.  Optional pointers may be NULL:
+ *   torques, res_f              -> treated as exact zeros (the reference multiplies them by 0, dp_model.py:529,536)
+ *   out_grf, out_jaf            -> force side channels at frame steps not written ([F,bs*nb,6] each)
+ */
+size_t ppr_rollout_workspace_bytes(ppr_model_t m, int64_t bs, int64_t nsteps);
+
+int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t frame_stride, float dt,
+                        const float* q_init,          /* [bs*nq] */
+                        const float* qd_init,         /* [bs*nqd] */
+                        const float* torques,         /* [T, bs*nqd] or NULL */
+                        const float* res_f,           /* [T, bs*nb, 6] or NULL */
+                        const float* refs,            /* [T, bs*nqd] */
+                        const float* target_ke,       /* [bs*nqd] */
+                        const float* target_kd,       /* [bs*nqd] */
+                        const float* body_inv_mass,   /* [bs*nb] */
+                        const float* body_inertia,    /* [bs*nb,3,3] */
+                        const float* body_inv_inertia,/* [bs*nb,3,3] */
+                        float* out_pos,               /* [F, bs*nb, 7] */
+                        float* out_vel,               /* [F, bs*nb, 6] */
+                        float* out_grf,               /* [F, bs*nb, 6] or NULL */
+                        float* out_jaf,               /* [F, bs*nb, 6] or NULL */
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* All adj_* outputs are OVERWRITTEN (not accumulated).  adj_torques / adj_res_f may be NULL.
+ * adj_body_mass of the reference is identically zero (integrate_bodies never uses `m`,
+ * integrator_euler.py:43) and is therefore not an output here. */
+int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t frame_stride, float dt,
+                         const float* q_init, const float* qd_init, const float* torques, const float* res_f,
+                         const float* refs, const float* target_ke, const float* target_kd,
+                         const float* body_inv_mass, const float* body_inertia, const float* body_inv_inertia,
+                         const float* adj_out_pos,    /* [F, bs*nb, 7] */
+                         const float* adj_out_vel,    /* [F, bs*nb, 6] */
+                         float* adj_q_init,           /* [bs*nq] */
+                         float* adj_qd_init,          /* [bs*nqd] */
+                         float* adj_torques,          /* [T, bs*nqd] or NULL */
+                         float* adj_res_f,            /* [T, bs*nb, 6] or NULL */
+                         float* adj_refs,             /* [T, bs*nqd] */
+                         float* adj_target_ke,        /* [bs*nqd] */
+                         float* adj_target_kd,        /* [bs*nqd] */
+                         float* adj_body_inv_mass,    /* [bs*nb] */
+                         float* adj_body_inertia,     /* [bs*nb,3,3] */
+                         float* adj_body_inv_inertia, /* [bs*nb,3,3] */
+                         const void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernels the library has launched since load (bench.py's gpu_launches). */
+int64_t ppr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPR_B200_H */
