@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the rollout hot path (forward + hand-written adjoint) on N B200s.
+
+    python bench.py --gpus 1 --steps K --warmup W                      # single GPU
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus N --steps K --warmup W     # CPU arm (rank 0 only)
+
+A "step" = one optimisation step of the hot path on one batch of synthetic input: ForwardWarp forward
+(one persistent rollout kernel), a quadratic pose loss, ForwardWarp backward (one adjoint kernel), torch autograd
+chaining the four mass-related gradients into body_mass (dp_model.py:725-730), and -- for N > 1 -- the single
+NCCL all-reduce of the packed shared-parameter gradients (target_ke, target_kd, body_mass).  1 env-step = one
+simulation substep of one environment.
+
+Workload (BASELINE.json configs[4], the scaling sweep, at its largest per-GPU size): laikago, 65 536 envs per GPU
+(weak scaling), 64 differentiated substeps per window, synthetic inputs (seed 0 + rank).  Other configs are
+parity-test cases; `--workload` selects them for ad-hoc measurements and `--extras` appends their numbers.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: robot, per-GPU envs, differentiated substeps, frame stride, clearance (m; <0 = penetrating), lin_vel
+    "laikago-scaling-65536x64": dict(robot="laikago", bs=65536, window=64, stride=32, clearance=1e-3, lin_vel=0.0),
+    "laikago-trot-64x760": dict(robot="laikago", bs=64, window=759, stride=33, clearance=1e-3, lin_vel=0.0),
+    "quad-1024x64": dict(robot="quad", bs=1024, window=64, stride=32, clearance=1e-3, lin_vel=0.0),
+    "human-4096x64-contact": dict(robot="human", bs=4096, window=64, stride=32, clearance=-0.0025, lin_vel=1.0),
+    "human-65536x64-contact": dict(robot="human", bs=65536, window=64, stride=32, clearance=-0.0025, lin_vel=1.0),
+}
+DEFAULT_WORKLOAD = "laikago-scaling-65536x64"
+DT = 5e-4
+
+
+def algorithmic_bytes(nb, nqd):
+    """S = nb*13*4 (body_q + body_qd), R = nqd*4. fwd = 2S+R, bwd = 3S+2R, fwd+bwd = 5S+3R."""
+    S, R = nb * 13 * 4, nqd * 4
+    return dict(fwd=2 * S + R, bwd=3 * S + 2 * R, fwdbwd=5 * S + 3 * R)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_measure(robot, window, stride, target_seconds=12.0, steps=1, warmup=0):
+    """Times the CPU port (oracle/cpu_port, OpenMP over envs, all host threads) on a bounded sample of the
+    workload: bs_sample envs x `window` substeps, forward + reverse sweep. Returns env-steps/s."""
+    import torch
+    from oracle.cpu_port import CpuRollout, num_threads
+    from ppr_diffphys_b200 import load_robot
+    rm = load_robot(robot)
+    cores = num_threads()
+    nsteps = window + 1
+    F = (nsteps - 1) // stride + 1
+
+    def make(bs):
+        g = torch.Generator().manual_seed(0)
+        B = rm.nqd - 6
+        ja = (torch.rand(bs, B, generator=g) * 2 - 1) * 0.2
+        q = torch.zeros(bs, rm.nq); q[:, 6] = 1.0; q[:, 7:] = ja
+        q[:, 1] = 0.45
+        refs = torch.zeros(nsteps, bs, rm.nqd); refs[:, :, 6:] = ja[None]
+        mass = torch.as_tensor(rm.body_mass)[None].repeat(bs, 1)
+        I = torch.as_tensor(rm.norm_body_inertia)[None] * mass[..., None, None]
+        return dict(q_init=q, qd_init=torch.randn(bs, rm.nqd, generator=g) * 0.1, torques=None, res_f=None, refs=refs,
+                    target_ke=torch.as_tensor(rm.joint_target_ke)[None].repeat(bs, 1).contiguous(),
+                    target_kd=torch.as_tensor(rm.joint_target_kd)[None].repeat(bs, 1).contiguous(),
+                    body_inv_mass=1.0 / mass, body_inertia=I.contiguous(), body_inv_inertia=torch.linalg.inv(I))
+
+    cpu = CpuRollout(rm)
+
+    def one(d):
+        t0 = time.perf_counter()
+        pos, vel = cpu.forward(d, DT, stride, F)
+        cpu.backward(pos * 0.01, vel * 0.01)
+        return time.perf_counter() - t0
+
+    probe_bs = 4 * cores
+    t_probe = one(make(probe_bs))
+    bs = int(max(cores, min(65536, probe_bs * target_seconds / max(t_probe, 1e-6) / max(1, steps + warmup))))
+    bs = max(cores, (bs // cores) * cores)
+    d = make(bs)
+    for _ in range(warmup):
+        one(d)
+    times = [one(d) for _ in range(max(1, steps))]
+    t = sum(times) / len(times)
+    return dict(value=bs * window / t, cores=cores, sample="%s, %d envs x %d substeps fwd+bwd, fp32 CPU port "
+                "(all %d contact points/env tested per substep like the reference), %d timed step(s), %.2f s/step"
+                % (robot, bs, window, rm.nc, len(times), t), ms_per_step=t * 1e3, bs=bs)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    r = cpu_measure(w["robot"], w["window"], w["stride"], target_seconds=20.0, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": "env_steps_per_sec_fwd_bwd", "value": r["value"], "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "robot": w["robot"], "substeps_per_window": w["window"],
+                   "note": "reference's Warp CPU device cannot be installed here (no network); this is the repo's "
+                           "C++/OpenMP port of the reference kernels on the box's host cores, bounded sample"},
+        "cpu_baseline": {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class Caller:
+    def __init__(self, env, num_envs, nsteps, stride):
+        self.env, self.num_envs, self.dt = env, num_envs, DT
+        self.steps_idx = range(nsteps)
+        self.frame2step = [i for i in range(nsteps) if i % stride == 0]
+        self.record_forces = False
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from ppr_diffphys_b200 import ForwardWarp, SimEnv, _lib, load_robot
+    from ppr_diffphys_b200.synth import make_batch, mass_chain
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOADS[args.workload]
+    bs = args.envs if args.envs else w["bs"]
+    window, stride = w["window"], w["stride"]
+    nsteps = window + 1
+    rm = load_robot(w["robot"])
+    env = SimEnv(rm)
+    nb, nqd = rm.nb, rm.nqd
+    caller = Caller(env, bs, nsteps, stride)
+    host = make_batch(env, bs, nsteps, seed=rank, clearance=w["clearance"], lin_vel=w["lin_vel"], pinned_host=True)
+    nI = torch.as_tensor(rm.norm_body_inertia, device=dev)
+    # shared parameters (what the reference optimises): PD gains + body mass; per-env replication like dp_model.py:723-725
+    p_ke = torch.as_tensor(rm.joint_target_ke, device=dev).clone().requires_grad_(True)
+    p_kd = torch.as_tensor(rm.joint_target_kd, device=dev).clone().requires_grad_(True)
+    p_mass = torch.as_tensor(rm.body_mass, device=dev).clone().requires_grad_(True)
+    packed = torch.zeros(2 * nqd + nb, device=dev)
+
+    def step(inp, need_loss_host):
+        """one optimisation step of the hot path on device-resident inputs"""
+        q_init = inp["q_init"].detach().requires_grad_(True)
+        qd_init = inp["qd_init"].detach().requires_grad_(True)
+        refs = inp["refs"].detach().requires_grad_(True)
+        ke = p_ke[None].expand(bs, nqd).reshape(-1)
+        kd = p_kd[None].expand(bs, nqd).reshape(-1)
+        mass = p_mass[None].expand(bs, nb).reshape(-1)
+        inv_m, I, inv_I = mass_chain(mass, nI)
+        pos, vel = ForwardWarp.apply(q_init, qd_init, None, None, refs, ke, kd, mass, inv_m, I, inv_I, caller)
+        loss = (pos[-1, :, :3] - pos[0, :, :3]).pow(2).mean() + 1e-3 * vel[-1].pow(2).mean()
+        for p in (p_ke, p_kd, p_mass):
+            p.grad = None
+        loss.backward()
+        packed[:nqd] = p_ke.grad
+        packed[nqd:2 * nqd] = p_kd.grad
+        packed[2 * nqd:] = p_mass.grad
+        if world > 1:
+            dist.all_reduce(packed)
+        if need_loss_host:
+            return float(loss), packed.cpu()
+        return loss, packed
+
+    dev_inp = {k: v.to(dev) for k, v in host.items()}
+    bytes_in = sum(host[k].numel() * 4 for k in ("q_init", "qd_init", "refs"))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    # ---- warm-up
+    for _ in range(max(3, args.warmup)):
+        step(dev_inp, False)
+    # ---- device-resident timing (value)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ms = timed(lambda: step(dev_inp, False), args.steps)
+    launches = _lib.launch_count() - n0
+    # ---- kernel-only timing with CUDA events on the launching stream (roofline)
+    ke = p_ke.detach()[None].expand(bs, nqd).reshape(-1).contiguous()
+    kd = p_kd.detach()[None].expand(bs, nqd).reshape(-1).contiguous()
+    mass = p_mass.detach()[None].expand(bs, nb).reshape(-1).contiguous()
+    inv_m, I, inv_I = mass_chain(mass, nI)
+    ws = None
+    evs = []
+    for i in range(args.steps + 1):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        pos, vel, _, _, ws = env.rollout_forward(bs, nsteps, stride, DT, dev_inp["q_init"], dev_inp["qd_init"], None,
+                                                 None, dev_inp["refs"], ke, kd, inv_m, I, inv_I, want_forces=False,
+                                                 workspace=ws)
+        e[1].record()
+        env.rollout_backward(bs, nsteps, stride, DT, dev_inp["q_init"], dev_inp["qd_init"], None, None,
+                             dev_inp["refs"], ke, kd, inv_m, I, inv_I, pos, vel, ws)
+        e[2].record()
+        evs.append(e)
+    torch.cuda.synchronize()
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in evs[1:]) / args.steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in evs[1:]) / args.steps
+    # ---- end-to-end: host (pinned) inputs -> device, step, loss + packed shared-parameter grads -> host
+    def e2e_step():
+        inp = {k: host[k].to(dev, non_blocking=True) for k in ("q_init", "qd_init", "refs")}
+        return step(inp, True)
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    env_steps = bs * window * world
+    ab = algorithmic_bytes(nb, nqd)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    bwd_gbs = ab["bwd"] * bs * window / (bwd_ms * 1e-3) / 1e9
+    fwd_gbs = ab["fwd"] * bs * window / (fwd_ms * 1e-3) / 1e9
+    value = env_steps / (ms / args.steps * 1e-3)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            r = cpu_measure(w["robot"], window, stride, target_seconds=10.0)
+            cpu = {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        except Exception as ex:  # the checker is optional for the GPU arm
+            cpu = {"value": None, "unit": "env-steps/s", "cores": None, "kind": "port", "sample": "failed: %r" % (ex,)}
+    line = {
+        "metric": "env_steps_per_sec_fwd_bwd", "value": value, "unit": "env-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "robot": w["robot"], "envs_per_gpu": bs, "substeps_per_window": window,
+                   "frame_stride": stride, "bodies": nb, "dofs": nqd, "contacts_per_env": rm.nc,
+                   "parallelism": "env-sharded x%d, 1 all-reduce of %d floats/step" % (world, 2 * nqd + nb),
+                   "l2": "working set >> 126 MB L2 (state checkpoint %.2f GB/step streamed once each way)"
+                         % (env.workspace_bytes(bs, nsteps) / 1e9)},
+        "gpu_launches": int(launches),
+        "kernels_ms": {"rollout_forward": fwd_ms, "rollout_backward": bwd_ms},
+        "fwd_only_env_steps_per_sec": bs * window / (fwd_ms * 1e-3),
+        "roofline": {"bound": "hbm", "kernel": "rollout_backward_kernel", "achieved": bwd_gbs, "peak": peak_gbs,
+                     "unit": "GB/s", "frac": bwd_gbs / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_env_step": ab,
+                     "forward_kernel": {"achieved": fwd_gbs, "frac": fwd_gbs / peak_gbs},
+                     "fwd_bwd_combined_frac": ab["fwdbwd"] * bs * window / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak_gbs,
+                     "note": "the path is FP32-issue / latency bound, not HBM bound (SURVEY.md 8d)"},
+        "e2e": {"value": env_steps / (ms_e2e / args.steps * 1e-3), "unit": "env-steps/s",
+                "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 4 + 4 * (2 * nqd + nb),
+                "ms_per_step": ms_e2e / args.steps},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

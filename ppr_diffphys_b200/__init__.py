@@ -10,3 +10,6 @@ library (``libppr_b200.so``) is missing -- there is no CPU fallback.
 from .model import RobotModel, compile_robot, load_robot, ROBOT_PRESETS  # noqa: F401
 
 __all__ = ["RobotModel", "compile_robot", "load_robot", "ROBOT_PRESETS"]
+from .ops import ForwardKinematics, ForwardWarp, SimEnv, convert_ppr_warp, LazyFrames  # noqa: E402,F401
+
+__all__ += ["ForwardKinematics", "ForwardWarp", "SimEnv", "convert_ppr_warp", "LazyFrames"]

@@ -1,0 +1,778 @@
+// sm_100a kernels + C ABI of the rollout hot path (see include/ppr_b200.h for the boundary and the reference
+// call sites each entry point replaces).
+//
+// Mapping: one LANE per rigid body, floor(32/nb) environments per warp (laikago 2x13, human 1x19, quad 1x26).
+// The body state (13 floats) lives in registers for the whole rollout; parent/child exchange of states and
+// wrenches is done with warp shuffles on the static articulation tree (no shared memory, no atomics ->
+// deterministic, unlike the reference's atomic_add/sub at integrator_euler.py:179,449,451).  The time loop is
+// inside the kernel: one launch per rollout instead of the reference's 4 launches + 1 memset + 2 clones per
+// substep (dp_model.py:1209-1228).  Per substep the forward kernel streams the state and the total body wrench
+// (19 floats / body) to an HBM checkpoint buffer laid out [t][warp][component][lane] (128-byte coalesced rows);
+// the backward kernel streams it back in reverse and recomputes every other intermediate.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+#include <vector>
+
+#include "../../include/ppr_b200.h"
+#include "ppr_body.h"
+
+using namespace ppr;
+typedef V3<float> F3;
+typedef Q4<float> F4;
+typedef Body<float> BodyF;
+typedef Wrench<float> WrenchF;
+
+#define PPR_MAX_CHILD 8
+#define PPR_CKPT_FLOATS 19  // body_q 7 + body_qd 6 + total wrench 6
+#define PPR_BLOCK 128
+#define FULL 0xffffffffu
+
+static std::atomic<int64_t> g_launches{0};
+
+// ----------------------------------------------------------------------------------------------- device model
+struct DevModel {
+    int nb, nq, nqd, nc, epw, maxc, maxdepth, big_threshold;
+    const int4* jinfo;        // [nb] type, parent, q_start, qd_start
+    const int4* jinfo2;       // [nb] ndof, depth, contact begin, contact end
+    const unsigned long long* child;  // [nb] 8 x uint8 child body index (0xff = none)
+    const float* xpj;         // [nb,7] joint_X_p
+    const float* qoff;        // [nb,4] rot(joint_X_c)
+    const float* axis;        // [nb,3]
+    const float* com;         // [nb,3]
+    const float4* lim;        // [nqd] lo, hi, lke, lkd
+    const float4* cpt;        // [nc] body-frame point xyz + dist, sorted by body
+    const int* cmat;          // [nc] material row
+    const float4* mats;       // [nshape] ke kd kf mu
+    const float* aabb;        // [nb,8] lo xyz, hi xyz, max dist, pad
+    float g[3], ake, akd;
+};
+
+struct ppr_model {
+    uint32_t magic;
+    int device;
+    DevModel d;
+    void* blob;               // one device allocation holding every array
+    size_t xpj_offset;        // byte offset of xpj inside blob
+    std::vector<float> h_xpj;
+};
+#define PPR_MAGIC 0x50505231u
+
+// ----------------------------------------------------------------------------------------------- lane helpers
+__device__ __forceinline__ float shf(float v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ F3 shf3(F3 v, int src) { return v3<float>(shf(v.x, src), shf(v.y, src), shf(v.z, src)); }
+__device__ __forceinline__ BodyF shf_body(const BodyF& b, int src) {
+    BodyF o;
+    o.x = shf3(b.x, src);
+    o.r = q4<float>(shf(b.r.x, src), shf(b.r.y, src), shf(b.r.z, src), shf(b.r.w, src));
+    o.w = shf3(b.w, src);
+    o.v = shf3(b.v, src);
+    return o;
+}
+__device__ __forceinline__ WrenchF shf_wrench(const WrenchF& w, int src) {
+    WrenchF o; o.t = shf3(w.t, src); o.f = shf3(w.f, src); return o;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+struct LaneInfo {
+    int env, body, parent_lane, type, ndof, depth, qs, qds, c0, c1;
+    bool valid, has_parent;
+    unsigned long long child;  // lane ids of children (0xff none)
+    JointStatic<float> js;
+    F3 com;
+    float aabb[7];
+};
+
+__device__ __forceinline__ LaneInfo lane_setup(const DevModel& M, int64_t warp, int lane, int64_t n_env) {
+    LaneInfo L;
+    int e_in_w = lane / M.nb;
+    int body = lane - e_in_w * M.nb;
+    int64_t env = warp * M.epw + e_in_w;
+    L.valid = (e_in_w < M.epw) && (env < n_env);
+    if (!L.valid) { e_in_w = 0; body = 0; env = warp * M.epw; }
+    int seg = e_in_w * M.nb;
+    L.env = (int)env; L.body = body;
+    int4 ji = M.jinfo[body], j2 = M.jinfo2[body];
+    L.type = ji.x; L.has_parent = ji.y >= 0; L.parent_lane = L.has_parent ? seg + ji.y : lane;
+    L.qs = ji.z; L.qds = ji.w; L.ndof = j2.x; L.depth = j2.y; L.c0 = j2.z; L.c1 = j2.w;
+    unsigned long long ch = M.child[body], out = 0;
+#pragma unroll
+    for (int s = 0; s < PPR_MAX_CHILD; ++s) {
+        unsigned c = (unsigned)((ch >> (8 * s)) & 0xffu);
+        unsigned long long v = (c == 0xffu || !L.valid) ? 0xffull : (unsigned long long)(seg + c);
+        out |= v << (8 * s);
+    }
+    L.child = out;
+    const float* xp = M.xpj + 7 * body;
+    L.js.type = L.type;
+    L.js.xpj = v3<float>(xp[0], xp[1], xp[2]);
+    L.js.qpj = q4<float>(xp[3], xp[4], xp[5], xp[6]);
+    L.js.qoff = q4<float>(M.qoff[4 * body], M.qoff[4 * body + 1], M.qoff[4 * body + 2], M.qoff[4 * body + 3]);
+    L.js.axis = v3<float>(M.axis[3 * body], M.axis[3 * body + 1], M.axis[3 * body + 2]);
+    L.com = v3<float>(M.com[3 * body], M.com[3 * body + 1], M.com[3 * body + 2]);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) L.aabb[i] = M.aabb[8 * body + i];
+    return L;
+}
+
+// lowest possible world-y of any contact point of this body (exact bound on the body-frame AABB; quat_rotate
+// is linear in the point even for non-unit quaternions)
+__device__ __forceinline__ bool contact_possible(const LaneInfo& L, const BodyF& s) {
+    float w = s.r.w, ux = s.r.x, uy = s.r.y, uz = s.r.z;
+    float m0 = 2.f * (w * uz + uy * ux), m1 = 2.f * w * w - 1.f + 2.f * uy * uy, m2 = 2.f * (uy * uz - w * ux);
+    float ylow = s.x.y + fminf(m0 * L.aabb[0], m0 * L.aabb[3]) + fminf(m1 * L.aabb[1], m1 * L.aabb[4]) +
+                 fminf(m2 * L.aabb[2], m2 * L.aabb[5]) - L.aabb[6];
+    return L.valid && (L.c1 > L.c0) && !(ylow > 1e-6f);
+}
+
+__device__ __forceinline__ ContactMat<float> load_mat(const DevModel& M, int k) {
+    float4 m = M.mats[M.cmat[k]];
+    ContactMat<float> c; c.ke = m.x; c.kd = m.y; c.kf = m.z; c.mu = m.w;
+    return c;
+}
+
+// K3 for the whole warp: subtracts contact wrenches from F (per lane = per body)
+__device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
+                                                  WrenchF& F) {
+    bool maybe = contact_possible(L, s);
+    bool big = (L.c1 - L.c0) > M.big_threshold;
+    if (maybe && !big) {
+        for (int k = L.c0; k < L.c1; ++k) {
+            float4 p = M.cpt[k];
+            contact_point_fwd(s, xc, v3<float>(p.x, p.y, p.z), p.w, load_mat(M, k), F);
+        }
+    }
+    unsigned mask = __ballot_sync(FULL, maybe && big);
+    while (mask) {
+        int a = __ffs(mask) - 1;
+        mask &= mask - 1;
+        BodyF sa = shf_body(s, a);
+        F3 xca = shf3(xc, a);
+        int c0 = __shfl_sync(FULL, L.c0, a), c1 = __shfl_sync(FULL, L.c1, a);
+        WrenchF W = wrench_zero<float>();
+        for (int k = c0 + lane; k < c1; k += 32) {
+            float4 p = M.cpt[k];
+            contact_point_fwd(sa, xca, v3<float>(p.x, p.y, p.z), p.w, load_mat(M, k), W);
+        }
+        W.t.x = warp_sum(W.t.x); W.t.y = warp_sum(W.t.y); W.t.z = warp_sum(W.t.z);
+        W.f.x = warp_sum(W.f.x); W.f.y = warp_sum(W.f.y); W.f.z = warp_sum(W.f.z);
+        if (lane == a) { F.t += W.t; F.f += W.f; }
+    }
+}
+
+// K3^T for the whole warp
+__device__ __forceinline__ void warp_contacts_adj(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
+                                                  const WrenchF& adjF, BodyF& adjS, F3& adj_xc) {
+    bool maybe = contact_possible(L, s);
+    bool big = (L.c1 - L.c0) > M.big_threshold;
+    if (maybe && !big) {
+        for (int k = L.c0; k < L.c1; ++k) {
+            float4 p = M.cpt[k];
+            contact_point_adj(s, xc, v3<float>(p.x, p.y, p.z), p.w, load_mat(M, k), adjF, adjS, adj_xc);
+        }
+    }
+    unsigned mask = __ballot_sync(FULL, maybe && big);
+    while (mask) {
+        int a = __ffs(mask) - 1;
+        mask &= mask - 1;
+        BodyF sa = shf_body(s, a);
+        F3 xca = shf3(xc, a);
+        WrenchF aFa = shf_wrench(adjF, a);
+        int c0 = __shfl_sync(FULL, L.c0, a), c1 = __shfl_sync(FULL, L.c1, a);
+        BodyF A = body_zero<float>();
+        F3 Axc = vzero<float>();
+        for (int k = c0 + lane; k < c1; k += 32) {
+            float4 p = M.cpt[k];
+            contact_point_adj(sa, xca, v3<float>(p.x, p.y, p.z), p.w, load_mat(M, k), aFa, A, Axc);
+        }
+        A.x.x = warp_sum(A.x.x); A.x.y = warp_sum(A.x.y); A.x.z = warp_sum(A.x.z);
+        A.r.x = warp_sum(A.r.x); A.r.y = warp_sum(A.r.y); A.r.z = warp_sum(A.r.z); A.r.w = warp_sum(A.r.w);
+        A.w.x = warp_sum(A.w.x); A.w.y = warp_sum(A.w.y); A.w.z = warp_sum(A.w.z);
+        A.v.x = warp_sum(A.v.x); A.v.y = warp_sum(A.v.y); A.v.z = warp_sum(A.v.z);
+        Axc.x = warp_sum(Axc.x); Axc.y = warp_sum(Axc.y); Axc.z = warp_sum(Axc.z);
+        if (lane == a) { body_acc(adjS, A); adj_xc += Axc; }
+    }
+}
+
+// articulation FK across the warp, level by level (parents before children)
+__device__ __forceinline__ BodyF warp_fk(const DevModel& M, const LaneInfo& L, const float* jq, const float* jqd) {
+    BodyF s = body_identity<float>();
+    for (int d = 0; d <= M.maxdepth; ++d) {
+        BodyF P = shf_body(s, L.parent_lane);
+        if (!L.has_parent) P = body_identity<float>();
+        if (L.depth == d) s = fk_joint_fwd(L.js, L.com, P, jq, jqd);
+    }
+    return s;
+}
+
+// sum over this lane's children of a Body-shaped quantity held by the child lanes
+__device__ __forceinline__ void gather_children_body(const DevModel& M, const LaneInfo& L, const BodyF& mine, BodyF& acc) {
+#pragma unroll
+    for (int sl = 0; sl < PPR_MAX_CHILD; ++sl) {
+        if (sl < M.maxc) {
+            unsigned c = (unsigned)((L.child >> (8 * sl)) & 0xffu);
+            BodyF o = shf_body(mine, c == 0xffu ? 0 : (int)c);
+            if (c != 0xffu) body_acc(acc, o);
+        }
+    }
+}
+
+__device__ __forceinline__ void load_joint_coords(const LaneInfo& L, const float* q, const float* qd, int nq, int nqd,
+                                                  float* jq, float* jqd) {
+    int ncoord = L.type == JT_FREE ? 7 : L.ndof;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) jq[k] = (k < ncoord) ? q[(int64_t)L.env * nq + L.qs + k] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) jqd[k] = (k < L.ndof) ? qd[(int64_t)L.env * nqd + L.qds + k] : 0.f;
+}
+
+// ----------------------------------------------------------------------------------------------- FK kernels
+__global__ void __launch_bounds__(PPR_BLOCK)
+fk_forward_kernel(DevModel M, int64_t n, const float* __restrict__ q, const float* __restrict__ qd,
+                  float* __restrict__ body_q, float* __restrict__ body_qd) {
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp * M.epw >= n) return;
+    LaneInfo L = lane_setup(M, warp, lane, n);
+    float jq[7], jqd[6];
+    load_joint_coords(L, q, qd, M.nq, M.nqd, jq, jqd);
+    BodyF s = warp_fk(M, L, jq, jqd);
+    if (L.valid) {
+        float* o = body_q + ((int64_t)L.env * M.nb + L.body) * 7;
+        o[0] = s.x.x; o[1] = s.x.y; o[2] = s.x.z; o[3] = s.r.x; o[4] = s.r.y; o[5] = s.r.z; o[6] = s.r.w;
+        float* v = body_qd + ((int64_t)L.env * M.nb + L.body) * 6;
+        v[0] = s.w.x; v[1] = s.w.y; v[2] = s.w.z; v[3] = s.v.x; v[4] = s.v.y; v[5] = s.v.z;
+    }
+}
+
+// shared by fk_backward_kernel and the tail of rollout_backward_kernel
+__device__ __forceinline__ void warp_fk_adjoint(const DevModel& M, const LaneInfo& L, const BodyF& s, BodyF adj,
+                                                const float* jq, const float* jqd, float* __restrict__ adj_q,
+                                                float* __restrict__ adj_qd) {
+    float ajq[7] = {0, 0, 0, 0, 0, 0, 0}, ajqd[6] = {0, 0, 0, 0, 0, 0};
+    for (int d = M.maxdepth; d >= 0; --d) {
+        BodyF P = shf_body(s, L.parent_lane);
+        if (!L.has_parent) P = body_identity<float>();
+        BodyF adjP = body_zero<float>();
+        if (L.depth == d) fk_joint_adj(L.js, L.com, P, jq, jqd, adj, adjP, ajq, ajqd);
+        gather_children_body(M, L, adjP, adj);
+    }
+    if (L.valid) {
+        int ncoord = L.type == JT_FREE ? 7 : L.ndof;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) if (k < ncoord) adj_q[(int64_t)L.env * M.nq + L.qs + k] = ajq[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k < L.ndof) adj_qd[(int64_t)L.env * M.nqd + L.qds + k] = ajqd[k];
+    }
+}
+
+__global__ void __launch_bounds__(PPR_BLOCK)
+fk_backward_kernel(DevModel M, int64_t n, const float* __restrict__ q, const float* __restrict__ qd,
+                   const float* __restrict__ adj_body_q, const float* __restrict__ adj_body_qd,
+                   float* __restrict__ adj_q, float* __restrict__ adj_qd) {
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp * M.epw >= n) return;
+    LaneInfo L = lane_setup(M, warp, lane, n);
+    float jq[7], jqd[6];
+    load_joint_coords(L, q, qd, M.nq, M.nqd, jq, jqd);
+    BodyF s = warp_fk(M, L, jq, jqd);
+    BodyF adj = body_zero<float>();
+    if (L.valid) {
+        const float* a = adj_body_q + ((int64_t)L.env * M.nb + L.body) * 7;
+        const float* b = adj_body_qd + ((int64_t)L.env * M.nb + L.body) * 6;
+        adj.x = v3<float>(a[0], a[1], a[2]); adj.r = q4<float>(a[3], a[4], a[5], a[6]);
+        adj.w = v3<float>(b[0], b[1], b[2]); adj.v = v3<float>(b[3], b[4], b[5]);
+    }
+    warp_fk_adjoint(M, L, s, adj, jq, jqd, adj_q, adj_qd);
+}
+
+// ----------------------------------------------------------------------------------------------- rollout
+struct RolloutArgs {
+    int64_t bs, nsteps, stride, nwarps;
+    float dt;
+    const float *q_init, *qd_init, *torques, *res_f, *refs, *ke, *kd, *inv_m, *I, *inv_I;
+    float *out_pos, *out_vel, *out_grf, *out_jaf;
+    float* ckpt;
+    // backward only
+    const float *adj_pos, *adj_vel;
+    float *adj_q_init, *adj_qd_init, *adj_torques, *adj_res_f, *adj_refs, *adj_ke, *adj_kd, *adj_inv_m, *adj_I,
+        *adj_inv_I;
+};
+
+__device__ __forceinline__ void load_ctl(const DevModel& M, const LaneInfo& L, const RolloutArgs& A, int64_t t,
+                                         const float* ke, const float* kd, JointCtl<float>& c) {
+    int64_t row = (t * A.bs + L.env) * M.nqd + L.qds;
+    bool on = L.type != JT_FREE;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        bool use = on && k < L.ndof;
+        c.target[k] = use ? A.refs[row + k] : 0.f;
+        c.act[k] = (use && A.torques) ? A.torques[row + k] : 0.f;
+        c.ke[k] = ke[k]; c.kd[k] = kd[k];
+    }
+}
+
+__device__ __forceinline__ void store_wrench_row(float* base, const WrenchF& w) {
+    base[0] = w.t.x; base[1] = w.t.y; base[2] = w.t.z; base[3] = w.f.x; base[4] = w.f.y; base[5] = w.f.z;
+}
+
+// forces of one substep; F = total wrench on this lane's body. Optionally exports the grf / jaf side channels.
+__device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
+                                            const JointCtl<float>& ctl, const float* res_f_row, float* grf_row,
+                                            float* jaf_row, WrenchF& F) {
+    F = wrench_zero<float>();
+    if (res_f_row && L.valid) {
+        F.t = v3<float>(res_f_row[0], res_f_row[1], res_f_row[2]);
+        F.f = v3<float>(res_f_row[3], res_f_row[4], res_f_row[5]);
+    }
+    warp_contacts_fwd(M, L, lane, s, xc, F);
+    WrenchF G = F;
+    if (grf_row && L.valid) store_wrench_row(grf_row, F);
+    // joints: this lane is the child of its joint
+    BodyF P = shf_body(s, L.parent_lane);
+    F3 xcp = shf3(xc, L.parent_lane);
+    if (!L.has_parent) { P = body_identity<float>(); xcp = vzero<float>(); }
+    F3 t, f, ap, ac;
+    joint_fwd(L.js, ctl, M.ake, M.akd, P, xcp, L.has_parent, s, xc, t, f, ap, ac);
+    WrenchF Wp = wrench_zero<float>();
+    if (L.type != JT_FREE) {
+        F.t -= t + cross(ac, f); F.f -= f;
+        if (L.has_parent) { Wp.t = t + cross(ap, f); Wp.f = f; }
+    }
+#pragma unroll
+    for (int sl = 0; sl < PPR_MAX_CHILD; ++sl) {
+        if (sl < M.maxc) {
+            unsigned c = (unsigned)((L.child >> (8 * sl)) & 0xffu);
+            WrenchF o = shf_wrench(Wp, c == 0xffu ? 0 : (int)c);
+            if (c != 0xffu) { F.t += o.t; F.f += o.f; }
+        }
+    }
+    if (jaf_row && L.valid) {
+        WrenchF J; J.t = F.t - G.t; J.f = F.f - G.f;
+        store_wrench_row(jaf_row, J);
+    }
+}
+
+__global__ void __launch_bounds__(PPR_BLOCK)
+rollout_forward_kernel(DevModel M, RolloutArgs A) {
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= A.nwarps) return;
+    LaneInfo L = lane_setup(M, warp, lane, A.bs);
+    // per-env parameters of this body / joint
+    int64_t eb = (int64_t)L.env * M.nb + L.body;
+    float inv_m = A.inv_m[eb];
+    float I[9], inv_I[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { I[i] = A.I[eb * 9 + i]; inv_I[i] = A.inv_I[eb * 9 + i]; }
+    JointCtl<float> ctl;
+    float ke[3], kd[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        bool use = L.type != JT_FREE && k < L.ndof;
+        int64_t d = (int64_t)L.env * M.nqd + L.qds + k;
+        ke[k] = use ? A.ke[d] : 0.f; kd[k] = use ? A.kd[d] : 0.f;
+        float4 lm = use ? M.lim[L.qds + k] : make_float4(-1e30f, 1e30f, 0.f, 0.f);
+        ctl.lo[k] = lm.x; ctl.hi[k] = lm.y; ctl.lke[k] = lm.z; ctl.lkd[k] = lm.w;
+    }
+    F3 g = v3<float>(M.g[0], M.g[1], M.g[2]);
+    float jq[7], jqd[6];
+    load_joint_coords(L, A.q_init, A.qd_init, M.nq, M.nqd, jq, jqd);
+    BodyF s = warp_fk(M, L, jq, jqd);
+
+    float* ck = A.ckpt + (warp * PPR_CKPT_FLOATS) * 32 + lane;
+    const int64_t ck_step = A.nwarps * PPR_CKPT_FLOATS * 32;
+    for (int64_t t = 0; t < A.nsteps; ++t) {
+        bool frame = (t % A.stride) == 0;
+        int64_t fi = t / A.stride;
+        int64_t frow = (fi * A.bs + L.env) * M.nb + L.body;
+        if (frame && L.valid) {
+            float* o = A.out_pos + frow * 7;
+            o[0] = s.x.x; o[1] = s.x.y; o[2] = s.x.z; o[3] = s.r.x; o[4] = s.r.y; o[5] = s.r.z; o[6] = s.r.w;
+            float* v = A.out_vel + frow * 6;
+            v[0] = s.w.x; v[1] = s.w.y; v[2] = s.w.z; v[3] = s.v.x; v[4] = s.v.y; v[5] = s.v.z;
+        }
+        // the substep past the last frame exists only for the force side channels (dp_model.py:397): skip it
+        // when nobody asked for them
+        if (t == A.nsteps - 1 && !A.out_grf && !A.out_jaf) break;
+        F3 xc = s.x + qrot(s.r, L.com);
+        load_ctl(M, L, A, t, ke, kd, ctl);
+        WrenchF F;
+        warp_forces(M, L, lane, s, xc, ctl, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
+                    (frame && A.out_grf) ? A.out_grf + frow * 6 : nullptr,
+                    (frame && A.out_jaf) ? A.out_jaf + frow * 6 : nullptr, F);
+        // checkpoint (coalesced: component-major rows of 32 lanes)
+        float* c = ck + t * ck_step;
+        c[0 * 32] = s.x.x; c[1 * 32] = s.x.y; c[2 * 32] = s.x.z;
+        c[3 * 32] = s.r.x; c[4 * 32] = s.r.y; c[5 * 32] = s.r.z; c[6 * 32] = s.r.w;
+        c[7 * 32] = s.w.x; c[8 * 32] = s.w.y; c[9 * 32] = s.w.z;
+        c[10 * 32] = s.v.x; c[11 * 32] = s.v.y; c[12 * 32] = s.v.z;
+        c[13 * 32] = F.t.x; c[14 * 32] = F.t.y; c[15 * 32] = F.t.z;
+        c[16 * 32] = F.f.x; c[17 * 32] = F.f.y; c[18 * 32] = F.f.z;
+        s = integrate_fwd(s, xc, L.com, F, inv_m, I, inv_I, g, A.dt);
+    }
+}
+
+__global__ void __launch_bounds__(PPR_BLOCK)
+rollout_backward_kernel(DevModel M, RolloutArgs A) {
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= A.nwarps) return;
+    LaneInfo L = lane_setup(M, warp, lane, A.bs);
+    int64_t eb = (int64_t)L.env * M.nb + L.body;
+    float inv_m = A.inv_m[eb];
+    float I[9], inv_I[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { I[i] = A.I[eb * 9 + i]; inv_I[i] = A.inv_I[eb * 9 + i]; }
+    JointCtl<float> ctl;
+    float ke[3], kd[3];
+    const bool jon = L.type != JT_FREE;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        bool use = jon && k < L.ndof;
+        int64_t d = (int64_t)L.env * M.nqd + L.qds + k;
+        ke[k] = use ? A.ke[d] : 0.f; kd[k] = use ? A.kd[d] : 0.f;
+        float4 lm = use ? M.lim[L.qds + k] : make_float4(-1e30f, 1e30f, 0.f, 0.f);
+        ctl.lo[k] = lm.x; ctl.hi[k] = lm.y; ctl.lke[k] = lm.z; ctl.lkd[k] = lm.w;
+    }
+    F3 g = v3<float>(M.g[0], M.g[1], M.g[2]);
+    // com of the parent body (to fold the parent's world-COM adjoint into its pose adjoint in the child lane)
+    F3 com_par = shf3(L.com, L.parent_lane);
+
+    float a_inv_m = 0.f, a_I[9], a_invI[9], a_ke[3] = {0, 0, 0}, a_kd[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { a_I[i] = 0.f; a_invI[i] = 0.f; }
+
+    const float* ck = A.ckpt + (warp * PPR_CKPT_FLOATS) * 32 + lane;
+    const int64_t ck_step = A.nwarps * PPR_CKPT_FLOATS * 32;
+    const int64_t last = A.nsteps - 1;
+
+    BodyF adjN = body_zero<float>();
+    // rows of the never-differentiated last substep (dp_model.py:397): zero gradient
+    if (L.valid) {
+        int64_t row = (last * A.bs + L.env) * M.nqd + L.qds;
+        for (int k = 0; k < L.ndof; ++k) {
+            A.adj_refs[row + k] = 0.f;
+            if (A.adj_torques) A.adj_torques[row + k] = 0.f;
+        }
+        if (A.adj_res_f) {
+            float* r = A.adj_res_f + ((last * A.bs + L.env) * M.nb + L.body) * 6;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) r[k] = 0.f;
+        }
+    }
+    for (int64_t t = last; t >= 0; --t) {
+        // seed from the loss at frame steps
+        if ((t % A.stride) == 0 && L.valid) {
+            int64_t frow = ((t / A.stride) * A.bs + L.env) * M.nb + L.body;
+            const float* a = A.adj_pos + frow * 7;
+            const float* b = A.adj_vel + frow * 6;
+            adjN.x += v3<float>(a[0], a[1], a[2]);
+            adjN.r += q4<float>(a[3], a[4], a[5], a[6]);
+            adjN.w += v3<float>(b[0], b[1], b[2]);
+            adjN.v += v3<float>(b[3], b[4], b[5]);
+        }
+        if (t == 0) break;
+        int64_t tp = t - 1;  // differentiate substep tp -> t
+        const float* c = ck + tp * ck_step;
+        BodyF s;
+        WrenchF F;
+        s.x = v3<float>(c[0 * 32], c[1 * 32], c[2 * 32]);
+        s.r = q4<float>(c[3 * 32], c[4 * 32], c[5 * 32], c[6 * 32]);
+        s.w = v3<float>(c[7 * 32], c[8 * 32], c[9 * 32]);
+        s.v = v3<float>(c[10 * 32], c[11 * 32], c[12 * 32]);
+        F.t = v3<float>(c[13 * 32], c[14 * 32], c[15 * 32]);
+        F.f = v3<float>(c[16 * 32], c[17 * 32], c[18 * 32]);
+        F3 xc = s.x + qrot(s.r, L.com);
+        load_ctl(M, L, A, tp, ke, kd, ctl);
+        // K5^T
+        BodyF adjS = body_zero<float>();
+        F3 adj_xc = vzero<float>();
+        WrenchF adjF;
+        integrate_adj(s, xc, L.com, F, inv_m, I, inv_I, g, A.dt, adjN, adjS, adj_xc, adjF, a_inv_m, a_I, a_invI);
+        // K4^T (this lane = child of its joint)
+        BodyF P = shf_body(s, L.parent_lane);
+        F3 xcp = shf3(xc, L.parent_lane);
+        WrenchF adjFp = shf_wrench(adjF, L.parent_lane);
+        if (!L.has_parent) { P = body_identity<float>(); xcp = vzero<float>(); adjFp = wrench_zero<float>(); }
+        BodyF adjP = body_zero<float>();
+        F3 adj_xcp = vzero<float>();
+        float g_target[3] = {0, 0, 0}, g_act[3] = {0, 0, 0};
+        joint_adj(L.js, ctl, M.ake, M.akd, P, xcp, L.has_parent, s, xc, adjFp, adjF, adjP, adj_xcp, adjS, adj_xc,
+                  g_target, g_act, a_ke, a_kd);
+        adjP.x += adj_xcp;
+        adjP.r += qrot_adj_q(P.r, com_par, adj_xcp);
+        if (!L.has_parent) adjP = body_zero<float>();
+        gather_children_body(M, L, adjP, adjS);
+        if (L.valid) {
+            int64_t row = (tp * A.bs + L.env) * M.nqd + L.qds;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) if (jon && k < L.ndof) {
+                A.adj_refs[row + k] = g_target[k];
+                if (A.adj_torques) A.adj_torques[row + k] = g_act[k];
+            }
+            if (!jon) for (int k = 0; k < L.ndof; ++k) {
+                A.adj_refs[row + k] = 0.f;
+                if (A.adj_torques) A.adj_torques[row + k] = 0.f;
+            }
+        }
+        // K3^T
+        warp_contacts_adj(M, L, lane, s, xc, adjF, adjS, adj_xc);
+        // K2^T
+        if (A.adj_res_f && L.valid) store_wrench_row(A.adj_res_f + ((tp * A.bs + L.env) * M.nb + L.body) * 6, adjF);
+        // world COM -> pose
+        adjS.x += adj_xc;
+        adjS.r += qrot_adj_q(s.r, L.com, adj_xc);
+        adjN = adjS;
+    }
+    // K1^T: state 0 = eval_fk(q_init, qd_init), recomputed
+    {
+        float jq[7], jqd[6];
+        load_joint_coords(L, A.q_init, A.qd_init, M.nq, M.nqd, jq, jqd);
+        BodyF s0 = warp_fk(M, L, jq, jqd);
+        warp_fk_adjoint(M, L, s0, adjN, jq, jqd, A.adj_q_init, A.adj_qd_init);
+    }
+    if (L.valid) {
+        A.adj_inv_m[eb] = a_inv_m;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { A.adj_I[eb * 9 + i] = a_I[i]; A.adj_inv_I[eb * 9 + i] = a_invI[i]; }
+        int64_t d = (int64_t)L.env * M.nqd + L.qds;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) if (jon && k < L.ndof) { A.adj_ke[d + k] = a_ke[k]; A.adj_kd[d + k] = a_kd[k]; }
+        if (!jon) for (int k = 0; k < L.ndof; ++k) { A.adj_ke[d + k] = 0.f; A.adj_kd[d + k] = 0.f; }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- host side
+static ppr_model* check(ppr_model_t m) { return (m && m->magic == PPR_MAGIC) ? m : nullptr; }
+
+extern "C" const char* ppr_version(void) { return "ppr_b200 0.1.0 (sm_100a)"; }
+extern "C" int64_t ppr_launch_count(void) { return g_launches.load(); }
+
+extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
+    if (!D || !out) return PPR_E_ARG;
+    if (D->nb < 1 || D->nb > 32 || D->nq < 1 || D->nqd < 0 || D->nc < 0 || D->nshape < 0) return PPR_E_SHAPE;
+    if (!D->joint_type || !D->joint_parent || !D->joint_q_start || !D->joint_qd_start || !D->joint_X_p ||
+        !D->joint_X_c || !D->joint_axis || !D->body_com)
+        return PPR_E_ARG;
+    if (D->nqd > 0 && (!D->joint_limit_lower || !D->joint_limit_upper || !D->joint_limit_ke || !D->joint_limit_kd))
+        return PPR_E_ARG;
+    if (D->nc > 0 && (!D->contact_body || !D->contact_point || !D->contact_dist || !D->contact_material ||
+                      !D->shape_materials))
+        return PPR_E_ARG;
+    const int nb = D->nb;
+    std::vector<int4> jinfo(nb), jinfo2(nb);
+    std::vector<unsigned long long> child(nb, ~0ull);
+    std::vector<int> nchild(nb, 0), depth(nb, 0);
+    int maxc = 0, maxdepth = 0;
+    for (int i = 0; i < nb; ++i) {
+        int p = D->joint_parent[i];
+        if (p >= i) return PPR_E_SHAPE;  // parents must precede children
+        int ty = D->joint_type[i];
+        int nd = (i + 1 < nb ? D->joint_qd_start[i + 1] : D->nqd) - D->joint_qd_start[i];
+        if (ty != JT_REVOLUTE && ty != JT_FIXED && ty != JT_FREE && ty != JT_COMPOUND) return PPR_E_SHAPE;
+        if ((ty == JT_FREE && nd != 6) || (ty == JT_REVOLUTE && nd != 1) || (ty == JT_COMPOUND && nd != 3) ||
+            (ty == JT_FIXED && nd != 0))
+            return PPR_E_SHAPE;
+        if (p >= 0) {
+            if (nchild[p] >= PPR_MAX_CHILD) return PPR_E_SHAPE;
+            child[p] &= ~(0xffull << (8 * nchild[p]));
+            child[p] |= (unsigned long long)i << (8 * nchild[p]);
+            nchild[p]++;
+            if (nchild[p] > maxc) maxc = nchild[p];
+            depth[i] = depth[p] + 1;
+            if (depth[i] > maxdepth) maxdepth = depth[i];
+        }
+        jinfo[i] = make_int4(ty, p, D->joint_q_start[i], D->joint_qd_start[i]);
+        jinfo2[i] = make_int4(nd, depth[i], 0, 0);
+    }
+    // contacts sorted by body (stable)
+    std::vector<float4> cpt;
+    std::vector<int> cmat;
+    std::vector<float> aabb(nb * 8, 0.f);
+    for (int b = 0; b < nb; ++b) {
+        int c0 = (int)cpt.size();
+        float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f}, dmax = 0.f;
+        for (int k = 0; k < D->nc; ++k) {
+            if (D->contact_body[k] != b) continue;
+            if (D->contact_material[k] < 0 || D->contact_material[k] >= D->nshape) return PPR_E_ARG;
+            const float* p = D->contact_point + 3 * k;
+            cpt.push_back(make_float4(p[0], p[1], p[2], D->contact_dist[k]));
+            cmat.push_back(D->contact_material[k]);
+            for (int i = 0; i < 3; ++i) { lo[i] = p[i] < lo[i] ? p[i] : lo[i]; hi[i] = p[i] > hi[i] ? p[i] : hi[i]; }
+            dmax = D->contact_dist[k] > dmax ? D->contact_dist[k] : dmax;
+        }
+        int c1 = (int)cpt.size();
+        jinfo2[b].z = c0; jinfo2[b].w = c1;
+        if (c1 > c0) { for (int i = 0; i < 3; ++i) { aabb[8 * b + i] = lo[i]; aabb[8 * b + 3 + i] = hi[i]; } aabb[8 * b + 6] = dmax; }
+    }
+    for (int k = 0; k < D->nc; ++k) if (D->contact_body[k] < 0 || D->contact_body[k] >= nb) return PPR_E_ARG;
+    std::vector<float4> lim(D->nqd > 0 ? D->nqd : 1);
+    for (int k = 0; k < D->nqd; ++k)
+        lim[k] = make_float4(D->joint_limit_lower[k], D->joint_limit_upper[k], D->joint_limit_ke[k], D->joint_limit_kd[k]);
+    std::vector<float> qoff(nb * 4);
+    for (int i = 0; i < nb; ++i) for (int k = 0; k < 4; ++k) qoff[4 * i + k] = D->joint_X_c[7 * i + 3 + k];
+
+    // pack into one blob
+    struct Seg { const void* src; size_t bytes; size_t off; };
+    std::vector<Seg> segs;
+    size_t total = 0;
+    auto add = [&](const void* p, size_t bytes) {
+        size_t off = (total + 255) & ~(size_t)255;
+        segs.push_back({p, bytes, off});
+        total = off + (bytes ? bytes : 16);
+        return off;
+    };
+    size_t o_jinfo = add(jinfo.data(), nb * sizeof(int4)), o_jinfo2 = add(jinfo2.data(), nb * sizeof(int4));
+    size_t o_child = add(child.data(), nb * sizeof(unsigned long long));
+    size_t o_xpj = add(D->joint_X_p, nb * 7 * sizeof(float)), o_qoff = add(qoff.data(), nb * 4 * sizeof(float));
+    size_t o_axis = add(D->joint_axis, nb * 3 * sizeof(float)), o_com = add(D->body_com, nb * 3 * sizeof(float));
+    size_t o_lim = add(lim.data(), lim.size() * sizeof(float4));
+    size_t o_cpt = add(cpt.data(), cpt.size() * sizeof(float4)), o_cmat = add(cmat.data(), cmat.size() * sizeof(int));
+    size_t o_mats = add(D->shape_materials, (size_t)D->nshape * 4 * sizeof(float));
+    size_t o_aabb = add(aabb.data(), aabb.size() * sizeof(float));
+
+    ppr_model* m = new (std::nothrow) ppr_model();
+    if (!m) return PPR_E_ARG;
+    cudaError_t e = cudaGetDevice(&m->device);
+    if (e != cudaSuccess) { delete m; return (int)e; }
+    e = cudaMalloc(&m->blob, total);
+    if (e != cudaSuccess) { delete m; return (int)e; }
+    std::vector<char> host(total, 0);
+    for (auto& s : segs) if (s.bytes) memcpy(host.data() + s.off, s.src, s.bytes);
+    e = cudaMemcpy(m->blob, host.data(), total, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(m->blob); delete m; return (int)e; }
+    char* base = (char*)m->blob;
+    DevModel& d = m->d;
+    d.nb = nb; d.nq = D->nq; d.nqd = D->nqd; d.nc = (int)cpt.size();
+    d.epw = 32 / nb; d.maxc = maxc; d.maxdepth = maxdepth; d.big_threshold = 16;
+    d.jinfo = (const int4*)(base + o_jinfo); d.jinfo2 = (const int4*)(base + o_jinfo2);
+    d.child = (const unsigned long long*)(base + o_child);
+    d.xpj = (const float*)(base + o_xpj); d.qoff = (const float*)(base + o_qoff);
+    d.axis = (const float*)(base + o_axis); d.com = (const float*)(base + o_com);
+    d.lim = (const float4*)(base + o_lim); d.cpt = (const float4*)(base + o_cpt); d.cmat = (const int*)(base + o_cmat);
+    d.mats = (const float4*)(base + o_mats); d.aabb = (const float*)(base + o_aabb);
+    d.g[0] = D->gravity[0]; d.g[1] = D->gravity[1]; d.g[2] = D->gravity[2];
+    d.ake = D->joint_attach_ke; d.akd = D->joint_attach_kd;
+    m->xpj_offset = o_xpj;
+    m->h_xpj.assign(D->joint_X_p, D->joint_X_p + nb * 7);
+    m->magic = PPR_MAGIC;
+    *out = m;
+    return 0;
+}
+
+extern "C" int ppr_model_destroy(ppr_model_t m) {
+    if (!check(m)) return PPR_E_HANDLE;
+    m->magic = 0;
+    cudaFree(m->blob);
+    delete m;
+    return 0;
+}
+
+extern "C" int ppr_model_set_joint_X_p(ppr_model_t m, const float* xp, void* stream) {
+    if (!check(m)) return PPR_E_HANDLE;
+    if (!xp) return PPR_E_ARG;
+    m->h_xpj.assign(xp, xp + m->d.nb * 7);
+    cudaError_t e = cudaMemcpyAsync((char*)m->blob + m->xpj_offset, m->h_xpj.data(), m->h_xpj.size() * sizeof(float),
+                                    cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    return (int)e;
+}
+extern "C" int ppr_model_set_attach(ppr_model_t m, float ke, float kd) {
+    if (!check(m)) return PPR_E_HANDLE;
+    m->d.ake = ke; m->d.akd = kd;
+    return 0;
+}
+extern "C" int ppr_model_set_gravity(ppr_model_t m, const float g[3]) {
+    if (!check(m)) return PPR_E_HANDLE;
+    if (!g) return PPR_E_ARG;
+    m->d.g[0] = g[0]; m->d.g[1] = g[1]; m->d.g[2] = g[2];
+    return 0;
+}
+extern "C" int ppr_model_envs_per_warp(ppr_model_t m) { return check(m) ? m->d.epw : PPR_E_HANDLE; }
+
+static inline int64_t nwarps_for(const DevModel& d, int64_t n) { return (n + d.epw - 1) / d.epw; }
+static inline unsigned grid_for(int64_t nwarps) { return (unsigned)((nwarps * 32 + PPR_BLOCK - 1) / PPR_BLOCK); }
+
+extern "C" int ppr_fk_forward(ppr_model_t m, int64_t n, const float* q, const float* qd, float* bq, float* bqd,
+                              void* stream) {
+    if (!check(m)) return PPR_E_HANDLE;
+    if (n < 0 || !q || !qd || !bq || !bqd) return PPR_E_ARG;
+    if (n == 0) return 0;
+    fk_forward_kernel<<<grid_for(nwarps_for(m->d, n)), PPR_BLOCK, 0, (cudaStream_t)stream>>>(m->d, n, q, qd, bq, bqd);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+extern "C" int ppr_fk_backward(ppr_model_t m, int64_t n, const float* q, const float* qd, const float* abq,
+                               const float* abqd, float* aq, float* aqd, void* stream) {
+    if (!check(m)) return PPR_E_HANDLE;
+    if (n < 0 || !q || !qd || !abq || !abqd || !aq || !aqd) return PPR_E_ARG;
+    if (n == 0) return 0;
+    fk_backward_kernel<<<grid_for(nwarps_for(m->d, n)), PPR_BLOCK, 0, (cudaStream_t)stream>>>(m->d, n, q, qd, abq, abqd,
+                                                                                                 aq, aqd);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+extern "C" size_t ppr_rollout_workspace_bytes(ppr_model_t m, int64_t bs, int64_t nsteps) {
+    if (!check(m) || bs <= 0 || nsteps <= 0) return 0;
+    return (size_t)nwarps_for(m->d, bs) * (size_t)nsteps * PPR_CKPT_FLOATS * 32 * sizeof(float);
+}
+
+extern "C" int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t stride, float dt,
+                                   const float* q_init, const float* qd_init, const float* torques, const float* res_f,
+                                   const float* refs, const float* ke, const float* kd, const float* inv_m,
+                                   const float* I, const float* inv_I, float* out_pos, float* out_vel, float* out_grf,
+                                   float* out_jaf, void* ws, size_t ws_bytes, void* stream) {
+    if (!check(m)) return PPR_E_HANDLE;
+    if (bs < 0 || nsteps < 1 || stride < 1) return PPR_E_ARG;
+    if (!q_init || !qd_init || !refs || !ke || !kd || !inv_m || !I || !inv_I || !out_pos || !out_vel || !ws)
+        return PPR_E_ARG;
+    if (bs == 0) return 0;
+    if (ws_bytes < ppr_rollout_workspace_bytes(m, bs, nsteps)) return PPR_E_WORKSPACE;
+    RolloutArgs A;
+    memset(&A, 0, sizeof(A));
+    A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.nwarps = nwarps_for(m->d, bs); A.dt = dt;
+    A.q_init = q_init; A.qd_init = qd_init; A.torques = torques; A.res_f = res_f; A.refs = refs; A.ke = ke; A.kd = kd;
+    A.inv_m = inv_m; A.I = I; A.inv_I = inv_I;
+    A.out_pos = out_pos; A.out_vel = out_vel; A.out_grf = out_grf; A.out_jaf = out_jaf; A.ckpt = (float*)ws;
+    rollout_forward_kernel<<<grid_for(A.nwarps), PPR_BLOCK, 0, (cudaStream_t)stream>>>(m->d, A);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+extern "C" int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t stride, float dt,
+                                    const float* q_init, const float* qd_init, const float* torques,
+                                    const float* res_f, const float* refs, const float* ke, const float* kd,
+                                    const float* inv_m, const float* I, const float* inv_I, const float* adj_pos,
+                                    const float* adj_vel, float* adj_q_init, float* adj_qd_init, float* adj_torques,
+                                    float* adj_res_f, float* adj_refs, float* adj_ke, float* adj_kd, float* adj_inv_m,
+                                    float* adj_I, float* adj_inv_I, const void* ws, size_t ws_bytes, void* stream) {
+    if (!check(m)) return PPR_E_HANDLE;
+    if (bs < 0 || nsteps < 1 || stride < 1) return PPR_E_ARG;
+    if (!q_init || !qd_init || !refs || !ke || !kd || !inv_m || !I || !inv_I || !adj_pos || !adj_vel || !adj_q_init ||
+        !adj_qd_init || !adj_refs || !adj_ke || !adj_kd || !adj_inv_m || !adj_I || !adj_inv_I || !ws)
+        return PPR_E_ARG;
+    if (bs == 0) return 0;
+    if (ws_bytes < ppr_rollout_workspace_bytes(m, bs, nsteps)) return PPR_E_WORKSPACE;
+    RolloutArgs A;
+    memset(&A, 0, sizeof(A));
+    A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.nwarps = nwarps_for(m->d, bs); A.dt = dt;
+    A.q_init = q_init; A.qd_init = qd_init; A.torques = torques; A.res_f = res_f; A.refs = refs; A.ke = ke; A.kd = kd;
+    A.inv_m = inv_m; A.I = I; A.inv_I = inv_I; A.ckpt = (float*)ws;
+    A.adj_pos = adj_pos; A.adj_vel = adj_vel; A.adj_q_init = adj_q_init; A.adj_qd_init = adj_qd_init;
+    A.adj_torques = adj_torques; A.adj_res_f = adj_res_f; A.adj_refs = adj_refs; A.adj_ke = adj_ke; A.adj_kd = adj_kd;
+    A.adj_inv_m = adj_inv_m; A.adj_I = adj_I; A.adj_inv_I = adj_inv_I;
+    rollout_backward_kernel<<<grid_for(A.nwarps), PPR_BLOCK, 0, (cudaStream_t)stream>>>(m->d, A);
+    g_launches++;
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,292 @@
+"""Drop-in replacements of the reference's simulator boundary (diffphys/dp_model.py:1014-1400).
+
+  convert_ppr_warp    dp_model.py:1014-1019
+  ForwardKinematics   dp_model.py:1022-1130   (Warp eval_fk under wp.Tape  ->  ppr_fk_forward / ppr_fk_backward)
+  ForwardWarp         dp_model.py:1145-1400   (per-substep Warp launches under wp.Tape  ->  ONE persistent rollout
+                                               kernel + ONE hand-written adjoint kernel)
+  SimEnv              the ``env`` object (reference: Warp ``Model`` built in reinit_envs, dp_model.py:384-401)
+
+Same call signatures, argument meaning, output shapes and side effects (``self.grfs``, ``self.jafs``,
+``self.sim_trajs``).  All device work goes through the C ABI in include/ppr_b200.h with raw pointers of torch
+tensors and torch's current stream; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._capi import make_desc
+from .model import RobotModel, load_robot
+
+
+def convert_ppr_warp(tensor):
+    """[linear, angular, ...] <-> [angular, linear, ...] (dp_model.py:1014-1019)."""
+    return torch.cat([tensor[..., 3:6], tensor[..., 0:3], tensor[..., 6:]], -1)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, device):
+    if t is None:
+        return None
+    if t.device != device:
+        t = t.to(device)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class LazyFrames:
+    """List-like view of per-frame numpy arrays (env 0) that copies to the host only when read; the reference
+    eagerly does ``.numpy()`` per frame (dp_model.py:1072,1244), forcing a sync on every forward."""
+
+    def __init__(self, tensor):  # [F, nb, 7] on device
+        self._t = tensor
+        self._np = None
+
+    def _get(self):
+        if self._np is None:
+            self._np = self._t.detach().cpu().numpy()
+        return self._np
+
+    def __len__(self):
+        return int(self._t.shape[0])
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def __iter__(self):
+        return iter(self._get())
+
+
+class SimEnv:
+    """Static model of one articulation shared by ``num_envs`` environments, resident on one GPU.
+
+    Mirrors what the reference reads from the Warp ``Model``: ``joint_X_p`` (mutable -- lab4d overwrites it,
+    dp_interface.py:465), ``joint_attach_ke/kd``, ``gravity``, ``ground`` and the body/joint/contact tables.
+    The reference replicates the tables num_envs times (dp_model.py:384-386); here ONE copy is uploaded."""
+
+    def __init__(self, robot, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.PprError("ppr_diffphys_b200 needs a CUDA device; there is no CPU fallback")
+        self.model: RobotModel = load_robot(robot) if isinstance(robot, str) else robot
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._lib = _lib.lib()
+        desc, keep = make_desc(self.model)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.ppr_model_create(C.byref(desc), C.byref(h)), "ppr_model_create")
+        self._h = h
+        self.ground = True
+        self.nb, self.nq, self.nqd = self.model.nb, self.model.nq, self.model.nqd
+        self.body_count_per_env = self.nb
+        self.joint_attach_ke = float(self.model.joint_attach_ke)
+        self.joint_attach_kd = float(self.model.joint_attach_kd)
+        self.body_com = torch.as_tensor(self.model.body_com)
+        self._joint_X_p = torch.as_tensor(self.model.joint_X_p).clone()
+
+    # -- mutable model attributes -----------------------------------------------------------------
+    @property
+    def joint_X_p(self):
+        return self._joint_X_p
+
+    @joint_X_p.setter
+    def joint_X_p(self, value):
+        v = torch.as_tensor(value).detach().float().cpu().reshape(-1, 7)[: self.nb].contiguous()
+        self._joint_X_p = v
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().synchronize()  # the host staging buffer is reused by the library
+            _lib.check(self._lib.ppr_model_set_joint_X_p(self._h, C.c_void_p(v.data_ptr()), _stream()),
+                       "ppr_model_set_joint_X_p")
+
+    def set_attach(self, ke, kd):
+        self.joint_attach_ke, self.joint_attach_kd = float(ke), float(kd)
+        _lib.check(self._lib.ppr_model_set_attach(self._h, C.c_float(ke), C.c_float(kd)), "ppr_model_set_attach")
+
+    def set_gravity(self, g):
+        arr = (C.c_float * 3)(*[float(x) for x in g])
+        _lib.check(self._lib.ppr_model_set_gravity(self._h, arr), "ppr_model_set_gravity")
+
+    @property
+    def envs_per_warp(self):
+        return int(self._lib.ppr_model_envs_per_warp(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.ppr_model_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- raw (non-autograd) entry points ------------------------------------------------------------
+    def fk(self, joint_q, joint_qd):
+        """joint_q [n,nq], joint_qd [n,nqd] -> body_q [n,nb,7], body_qd [n,nb,6]."""
+        n = joint_q.shape[0]
+        bq = torch.empty(n, self.nb, 7, device=self.device, dtype=torch.float32)
+        bqd = torch.empty(n, self.nb, 6, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.ppr_fk_forward(self._h, n, _ptr(joint_q), _ptr(joint_qd), _ptr(bq), _ptr(bqd),
+                                                _stream()), "ppr_fk_forward")
+        return bq, bqd
+
+    def fk_backward(self, joint_q, joint_qd, adj_bq, adj_bqd):
+        n = joint_q.shape[0]
+        aq = torch.empty(n, self.nq, device=self.device, dtype=torch.float32)
+        aqd = torch.empty(n, self.nqd, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.ppr_fk_backward(self._h, n, _ptr(joint_q), _ptr(joint_qd), _ptr(adj_bq),
+                                                 _ptr(adj_bqd), _ptr(aq), _ptr(aqd), _stream()), "ppr_fk_backward")
+        return aq, aqd
+
+    def workspace_bytes(self, bs, nsteps):
+        return int(self._lib.ppr_rollout_workspace_bytes(self._h, bs, nsteps))
+
+    def rollout_forward(self, bs, nsteps, stride, dt, q_init, qd_init, torques, res_f, refs, ke, kd, inv_m, I, inv_I,
+                        want_forces=True, workspace=None):
+        F = (nsteps - 1) // stride + 1
+        dev = self.device
+        pos = torch.empty(F, bs * self.nb, 7, device=dev, dtype=torch.float32)
+        vel = torch.empty(F, bs * self.nb, 6, device=dev, dtype=torch.float32)
+        grf = torch.empty(F, bs * self.nb, 6, device=dev, dtype=torch.float32) if want_forces else None
+        jaf = torch.empty(F, bs * self.nb, 6, device=dev, dtype=torch.float32) if want_forces else None
+        nbytes = self.workspace_bytes(bs, nsteps)
+        if workspace is None or workspace.numel() * workspace.element_size() < nbytes:
+            workspace = torch.empty((nbytes + 3) // 4, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.ppr_rollout_forward(
+                self._h, bs, nsteps, stride, C.c_float(dt), _ptr(q_init), _ptr(qd_init), _ptr(torques), _ptr(res_f),
+                _ptr(refs), _ptr(ke), _ptr(kd), _ptr(inv_m), _ptr(I), _ptr(inv_I), _ptr(pos), _ptr(vel), _ptr(grf),
+                _ptr(jaf), _ptr(workspace), C.c_size_t(workspace.numel() * 4), _stream()), "ppr_rollout_forward")
+        return pos, vel, grf, jaf, workspace
+
+    def rollout_backward(self, bs, nsteps, stride, dt, q_init, qd_init, torques, res_f, refs, ke, kd, inv_m, I, inv_I,
+                         adj_pos, adj_vel, workspace):
+        dev = self.device
+        e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        g = dict(q_init=e(bs * self.nq), qd_init=e(bs * self.nqd),
+                 torques=e(nsteps, bs * self.nqd) if torques is not None else None,
+                 res_f=e(nsteps, bs * self.nb, 6) if res_f is not None else None,
+                 refs=e(nsteps, bs * self.nqd), target_ke=e(bs * self.nqd), target_kd=e(bs * self.nqd),
+                 body_inv_mass=e(bs * self.nb), body_inertia=e(bs * self.nb, 3, 3),
+                 body_inv_inertia=e(bs * self.nb, 3, 3))
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.ppr_rollout_backward(
+                self._h, bs, nsteps, stride, C.c_float(dt), _ptr(q_init), _ptr(qd_init), _ptr(torques), _ptr(res_f),
+                _ptr(refs), _ptr(ke), _ptr(kd), _ptr(inv_m), _ptr(I), _ptr(inv_I), _ptr(adj_pos), _ptr(adj_vel),
+                _ptr(g["q_init"]), _ptr(g["qd_init"]), _ptr(g["torques"]), _ptr(g["res_f"]), _ptr(g["refs"]),
+                _ptr(g["target_ke"]), _ptr(g["target_kd"]), _ptr(g["body_inv_mass"]), _ptr(g["body_inertia"]),
+                _ptr(g["body_inv_inertia"]), _ptr(workspace), C.c_size_t(workspace.numel() * 4), _stream()),
+                "ppr_rollout_backward")
+        return g
+
+
+def _scrub(g):
+    """remove_nan (dp_utils.py:43-57, clip=False): NaN -> 0."""
+    return None if g is None else torch.nan_to_num(g, nan=0.0, posinf=float("inf"), neginf=float("-inf"))
+
+
+class ForwardKinematics(torch.autograd.Function):
+    """``ForwardKinematics.apply(rj_q[T,bs,7+B], rj_qd[T,bs,6+B], env) -> (body_q[bs,T,nb,7], body_qd[bs,T,nb,6],
+    body_q_numpy)`` -- dp_model.py:1022-1130. One launch for all T frames (reference: T launches + T State allocs)."""
+
+    @staticmethod
+    def forward(ctx, rj_q, rj_qd, env):
+        is_cuda = rj_q.is_cuda
+        T, bs, nq = rj_q.shape
+        q = _f32c(rj_q, env.device).reshape(T * bs, nq)
+        if rj_qd is None:
+            qd = torch.zeros(T * bs, nq - 1, device=env.device, dtype=torch.float32)
+        else:
+            qd = _f32c(rj_qd, env.device).reshape(T * bs, nq - 1)
+        bq, bqd = env.fk(q, qd)
+        ctx.env, ctx.shape, ctx.is_cuda = env, (T, bs, nq), is_cuda
+        ctx.save_for_backward(q, qd)
+        body_q = bq.view(T, bs, env.nb, 7).permute(1, 0, 2, 3).contiguous()
+        body_qd = bqd.view(T, bs, env.nb, 6).permute(1, 0, 2, 3).contiguous()
+        body_q_numpy = LazyFrames(body_q[0])
+        if not is_cuda:
+            body_q, body_qd = body_q.cpu(), body_qd.cpu()
+        return body_q, body_qd, body_q_numpy
+
+    @staticmethod
+    def backward(ctx, adj_body_q, adj_body_qd, _):
+        env = ctx.env
+        T, bs, nq = ctx.shape
+        q, qd = ctx.saved_tensors
+        z = lambda a, c: torch.zeros(bs, T, env.nb, c, device=env.device) if a is None else a
+        aq = _f32c(z(adj_body_q, 7), env.device).permute(1, 0, 2, 3).contiguous().view(T * bs, env.nb, 7)
+        aqd = _f32c(z(adj_body_qd, 6), env.device).permute(1, 0, 2, 3).contiguous().view(T * bs, env.nb, 6)
+        gq, gqd = env.fk_backward(q, qd, aq, aqd)
+        # reference post-processing (dp_model.py:1109-1110,1122-1123): NaN -> 0, upper clamp at +1 only
+        gq = torch.nan_to_num(gq, nan=0.0).clamp(max=1.0).view(T, bs, nq)
+        gqd = torch.nan_to_num(gqd, nan=0.0).clamp(max=1.0).view(T, bs, nq - 1)
+        if not ctx.is_cuda:
+            gq, gqd = gq.cpu(), gqd.cpu()
+        return (gq if ctx.needs_input_grad[0] else None, gqd if ctx.needs_input_grad[1] else None, None)
+
+
+class ForwardWarp(torch.autograd.Function):
+    """``ForwardWarp.apply(q_init, qd_init, torques, res_f, refs, target_ke, target_kd, body_mass, body_inv_mass,
+    body_inertia, body_inv_inertia, self) -> (wp_pos[F,bs*nb,7], wp_vel[F,bs*nb,6])`` -- dp_model.py:1145-1400.
+
+    ``self`` is the caller object of the reference (``phys_model``): it must expose ``env`` (a SimEnv),
+    ``num_envs``, ``steps_idx``, ``frame2step`` and ``dt``; ``grfs``, ``jafs`` and ``sim_trajs`` are written onto
+    it exactly like the reference does (dp_model.py:1207-1208,1233-1234,1237,1244).  ``torques`` / ``res_f`` may be
+    None (exact zeros -- the reference multiplies them by 0, dp_model.py:529,536)."""
+
+    @staticmethod
+    def forward(ctx, q_init, qd_init, torques, res_f, refs, target_ke, target_kd, body_mass, body_inv_mass,
+                body_inertia, body_inv_inertia, self):
+        env: SimEnv = self.env
+        dev = env.device
+        bs = int(self.num_envs)
+        nsteps = len(self.steps_idx)
+        f2s = list(self.frame2step)
+        stride = (f2s[1] - f2s[0]) if len(f2s) > 1 else nsteps
+        assert all(s == i * stride for i, s in enumerate(f2s)), "frame2step must be evenly strided"
+        a = dict(q_init=_f32c(q_init, dev), qd_init=_f32c(qd_init, dev), torques=_f32c(torques, dev),
+                 res_f=_f32c(res_f, dev), refs=_f32c(refs, dev), ke=_f32c(target_ke, dev), kd=_f32c(target_kd, dev),
+                 inv_m=_f32c(body_inv_mass, dev), I=_f32c(body_inertia, dev), inv_I=_f32c(body_inv_inertia, dev))
+        assert a["q_init"].numel() == bs * env.nq and a["qd_init"].numel() == bs * env.nqd
+        assert a["refs"].numel() == nsteps * bs * env.nqd
+        want_forces = bool(getattr(self, "record_forces", True))
+        pos, vel, grf, jaf, ws = env.rollout_forward(bs, nsteps, stride, float(self.dt), a["q_init"], a["qd_init"],
+                                                     a["torques"], a["res_f"], a["refs"], a["ke"], a["kd"],
+                                                     a["inv_m"], a["I"], a["inv_I"], want_forces=want_forces)
+        F = pos.shape[0]
+        self.grfs = [grf[i] for i in range(F)] if want_forces else []
+        self.jafs = [jaf[i] for i in range(F)] if want_forces else []
+        self.sim_trajs = LazyFrames(pos[:, : env.nb])
+        ctx.args, ctx.ws, ctx.env, ctx.dims = a, ws, env, (bs, nsteps, stride, float(self.dt))
+        ctx.shapes = dict(q_init=q_init.shape, qd_init=qd_init.shape, refs=refs.shape,
+                          torques=None if torques is None else torques.shape,
+                          res_f=None if res_f is None else res_f.shape, ke=target_ke.shape, kd=target_kd.shape,
+                          mass=body_mass.shape, inv_m=body_inv_mass.shape, I=body_inertia.shape,
+                          inv_I=body_inv_inertia.shape)
+        return pos, vel
+
+    @staticmethod
+    def backward(ctx, adj_body_qs, adj_body_qd):
+        env, a = ctx.env, ctx.args
+        bs, nsteps, stride, dt = ctx.dims
+        g = env.rollout_backward(bs, nsteps, stride, dt, a["q_init"], a["qd_init"], a["torques"], a["res_f"],
+                                 a["refs"], a["ke"], a["kd"], a["inv_m"], a["I"], a["inv_I"],
+                                 _f32c(adj_body_qs, env.device), _f32c(adj_body_qd, env.device), ctx.ws)
+        need, sh = ctx.needs_input_grad, ctx.shapes
+        pick = lambda i, t, shape: _scrub(t).view(shape) if (need[i] and t is not None) else None
+        body_mass_grad = torch.zeros(sh["mass"], device=env.device) if need[7] else None  # K5 never reads m
+        return (pick(0, g["q_init"], sh["q_init"]), pick(1, g["qd_init"], sh["qd_init"]),
+                pick(2, g["torques"], sh["torques"]), pick(3, g["res_f"], sh["res_f"]),
+                pick(4, g["refs"], sh["refs"]), pick(5, g["target_ke"], sh["ke"]), pick(6, g["target_kd"], sh["kd"]),
+                body_mass_grad, pick(8, g["body_inv_mass"], sh["inv_m"]), pick(9, g["body_inertia"], sh["I"]),
+                pick(10, g["body_inv_inertia"], sh["inv_I"]), None)

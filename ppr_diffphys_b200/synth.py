@@ -1,0 +1,63 @@
+"""Synthetic batched rollout inputs on the device: root at standing height,
+identity orientation + N(0,0.01) quaternion noise (renormalised), joint angles U(-a,a), qd_init N(0,0.1),
+refs = joint angles + 0.1 sin(2 pi t / 64 + phi_j); masses / inertias / PD gains from the compiled robot.
+Returned tensors use the reference's flattened call layout of ForwardWarp.apply (dp_model.py:563-572,697-699)."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+def _quat_rotate(q, v):
+    u, w = q[..., :3], q[..., 3:]
+    return v * (2.0 * w * w - 1.0) + 2.0 * w * torch.cross(u, v, dim=-1) + 2.0 * u * (u * v).sum(-1, keepdim=True)
+
+
+def make_batch(env, bs, nsteps, seed=0, clearance=1e-3, ang=0.2, qd_std=0.1, ref_amp=0.1, lin_vel=0.0,
+               pinned_host=False):
+    """env: SimEnv. clearance > 0: lowest contact point that far ABOVE ground; < 0: penetrating."""
+    rm, dev = env.model, env.device
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    nb, nq, nqd = rm.nb, rm.nq, rm.nqd
+    B = nqd - 6
+    ja = (torch.rand(bs, B, generator=g) * 2 - 1) * ang
+    quat = torch.tensor([0.0, 0, 0, 1.0]).expand(bs, 4) + torch.randn(bs, 4, generator=g) * 0.01
+    quat = quat / quat.norm(dim=-1, keepdim=True)
+    pos = torch.zeros(bs, 3)
+    q_init = torch.cat([pos, quat, ja], -1)
+    qd_init = torch.randn(bs, nqd, generator=g) * qd_std
+    if lin_vel > 0:
+        qd_init[:, 3] = (torch.rand(bs, generator=g) * 2 - 1) * lin_vel
+        qd_init[:, 5] = (torch.rand(bs, generator=g) * 2 - 1) * lin_vel
+    # settle the root height with the library's own FK
+    bq, _ = env.fk(q_init.to(dev), torch.zeros(bs, nqd, device=dev))
+    cb = torch.as_tensor(rm.contact_body, dtype=torch.long, device=dev)
+    cp = torch.as_tensor(rm.contact_point, device=dev)
+    cd = torch.as_tensor(rm.contact_dist, device=dev)
+    X = bq[:, cb]
+    y = (X[..., :3] + _quat_rotate(X[..., 3:7], cp[None]))[..., 1] - cd[None]
+    q_init[:, 1] = (-y.min(dim=1)[0] + clearance).cpu()
+    t = torch.arange(nsteps, dtype=torch.float32)[:, None, None]
+    phase = torch.rand(1, bs, B, generator=g) * 2 * math.pi
+    refs = torch.zeros(nsteps, bs, nqd)
+    refs[:, :, 6:] = ja[None] + ref_amp * torch.sin(2 * math.pi * t / 64.0 + phase)
+    ke = torch.as_tensor(rm.joint_target_ke)[None].repeat(bs, 1)
+    kd = torch.as_tensor(rm.joint_target_kd)[None].repeat(bs, 1)
+    mass = torch.as_tensor(rm.body_mass)[None].repeat(bs, 1)
+    host = dict(q_init=q_init.reshape(-1), qd_init=qd_init.reshape(-1), refs=refs.reshape(nsteps, -1),
+                target_ke=ke.reshape(-1), target_kd=kd.reshape(-1), body_mass=mass.reshape(-1))
+    host = {k: v.float().contiguous() for k, v in host.items()}
+    if pinned_host:
+        host = {k: v.pin_memory() for k, v in host.items()}
+    return host
+
+
+def mass_chain(body_mass, norm_body_inertia):
+    """body_mass [bs*nb] -> inv_mass, inertia, inv_inertia exactly like dp_model.py:725-730 (differentiable)."""
+    nI = norm_body_inertia
+    bs = body_mass.numel() // nI.shape[0]
+    inv_m = 1.0 / body_mass
+    I = nI[None].repeat(bs, 1, 1, 1).view(-1, 3, 3) * body_mass[..., None, None]
+    inv_I = torch.linalg.inv(I).contiguous()
+    return inv_m, I, inv_I

@@ -57,3 +57,17 @@ def standing_height(rm, q_rot=None, margin=1e-3, ja=None):
     bq, _ = eval_fk(m, q, torch.zeros(1, rm.nqd, dtype=torch.float64))
     cp = transform_point(bq[:, m.contact_body], m.contact_point[None])
     return float(-(cp[..., 1] - m.contact_dist[None]).min() + margin)
+
+
+def settle_height(rm, d, penetration=0.003):
+    """Shift every env's root height so that its lowest contact point penetrates the ground by ``penetration``
+    (uses the actual initial joint angles / root orientation)."""
+    from oracle.sim_oracle import OracleModel, eval_fk, transform_point
+    m = OracleModel(rm)
+    q = d["q_init"].double().clone()
+    bq, _ = eval_fk(m, q, torch.zeros(q.shape[0], rm.nqd, dtype=torch.float64))
+    cp = transform_point(bq[:, m.contact_body], m.contact_point[None])
+    low = (cp[..., 1] - m.contact_dist[None]).min(dim=1)[0]
+    q[:, 1] = q[:, 1] - low - penetration
+    d["q_init"] = q.to(d["q_init"].dtype)
+    return d
