@@ -8,7 +8,7 @@ import os
 from ._capi import ModelDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libppr_b200.so")
+LIB_PATH = os.environ.get("PPR_B200_LIB") or os.path.join(_HERE, "libppr_b200.so")  # env override: A/B builds
 _lib = None
 
 _vp, _i64, _f32 = C.c_void_p, C.c_int64, C.c_float

@@ -43,6 +43,19 @@ template <class T> struct JointCtl {  // per-dof quantities of one joint (up to 
 };
 template <class T> struct ContactMat { T ke, kd, kf, mu; };
 
+// Compile-time feature set of an articulation, so that a kernel instance only carries the code its robot needs
+// (the generic adjoint is ~18k SASS instructions and thrashes the instruction cache):
+//   JM_REVOLUTE: FREE + REVOLUTE joints only (laikago);  JM_COMPOUND: FREE + COMPOUND only (human, quad);
+//   JM_ALL: every supported type.  LIMITS: joint limit springs present.  QOFF: some COMPOUND joint has a
+//   non-identity joint_X_c rotation.
+enum JointMode { JM_REVOLUTE = 0, JM_COMPOUND = 1, JM_ALL = 2 };
+template <int JM> PPR_HD bool jm_has(int type) {
+    if (type == JT_FREE) return true;
+    if (type == JT_REVOLUTE) return JM != JM_COMPOUND;
+    if (type == JT_COMPOUND) return JM != JM_REVOLUTE;
+    return JM == JM_ALL;
+}
+
 // ------------------------------------------------------------------------------------------ contacts (K3)
 // Subtracts the ground-contact wrench of one contact point from F. xc = world COM of the body.
 template <class T>
@@ -129,7 +142,7 @@ PPR_HD T joint_limit_force(T q, T qd, T lo, T hi, T lke, T lkd) {
     return lim;
 }
 // adjoint of sc = ke(q-target) + kd qd + act - lim, given g = adj_sc
-template <class T>
+template <class T, bool LIMITS = true>
 PPR_HD void joint_scalar_adj(T q, T qd, const JointCtl<T>& c, int k, T g, T& g_q, T& g_qd, T* adj_target, T* adj_act,
                              T* adj_ke, T* adj_kd) {
     g_q += c.ke[k] * g;
@@ -138,6 +151,7 @@ PPR_HD void joint_scalar_adj(T q, T qd, const JointCtl<T>& c, int k, T g, T& g_q
     adj_act[k] += g;
     adj_ke[k] += (q - c.target[k]) * g;
     adj_kd[k] += qd * g;
+    if (!LIMITS) return;
     T g_lim = -g;
     if (q > c.hi[k]) {
         g_q += -c.lke[k] * g_lim;
@@ -172,7 +186,7 @@ template <class T> PPR_HD void revolute_angle_adj(V3<T> axis, Q4<T> r_err, T g_q
 // Forward joint wrench. P = parent body (identity / zero twist if the joint has no parent), xcp / xcc = world COMs.
 // Outputs the joint torque t and force f together with the two moment arms; the caller applies
 //   F_parent += (t + arm_p x f, f),  F_child -= (t + arm_c x f, f)      (integrator_euler.py:448-451)
-template <class T>
+template <class T, int JM = JM_ALL, bool LIMITS = true, bool QOFF = true>
 PPR_HD void joint_fwd(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T akd, const Body<T>& P, V3<T> xcp,
                       bool has_parent, const Body<T>& C, V3<T> xcc, V3<T>& t_out, V3<T>& f_out, V3<T>& arm_p,
                       V3<T>& arm_c) {
@@ -186,16 +200,16 @@ PPR_HD void joint_fwd(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
     Q4<T> r_err = qmul(qconj(qA), C.r);
     V3<T> v_err = C.v - P.v, w_err = C.w - P.w;
     const T ads = T(0.01);
-    if (js.type == JT_REVOLUTE) {
+    if (JM != JM_COMPOUND && js.type == JT_REVOLUTE) {
         V3<T> axis_p = qrot(qA, js.axis), axis_c = qrot(C.r, js.axis);
         T q = revolute_angle(js.axis, r_err);
         T qd = dot(w_err, axis_p);
         T sc = c.ke[0] * (q - c.target[0]) + c.kd[0] * qd + c.act[0] -
-               joint_limit_force(q, qd, c.lo[0], c.hi[0], c.lke[0], c.lkd[0]);
+               (LIMITS ? joint_limit_force(q, qd, c.lo[0], c.hi[0], c.lke[0], c.lkd[0]) : T(0));
         t_out = axis_p * sc + cross(axis_p, axis_c) * ake + (w_err - axis_p * qd) * (akd * ads);
         f_out = x_err * ake + v_err * akd;
-    } else if (js.type == JT_COMPOUND) {
-        Q4<T> q_pc = qmul(qmul(qconj(js.qoff), r_err), js.qoff);
+    } else if (JM != JM_REVOLUTE && js.type == JT_COMPOUND) {
+        Q4<T> q_pc = QOFF ? qmul(qmul(qconj(js.qoff), r_err), js.qoff) : r_err;
         V3<T> c0 = qrot(q_pc, v3<T>(T(1), T(0), T(0)));
         V3<T> c1 = qrot(q_pc, v3<T>(T(0), T(1), T(0)));
         V3<T> c2 = qrot(q_pc, v3<T>(T(0), T(0), T(1)));
@@ -205,7 +219,7 @@ PPR_HD void joint_fwd(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
         V3<T> a1 = qrot(q0, v3<T>(T(0), T(1), T(0)));
         Q4<T> q1 = q_axis_angle(a1, ang[1]);
         V3<T> a2 = qrot(qmul(q1, q0), v3<T>(T(0), T(0), T(1)));
-        Q4<T> qw = qmul(qA, js.qoff);
+        Q4<T> qw = QOFF ? qmul(qA, js.qoff) : qA;
         V3<T> ax[3] = {a0, a1, a2};
         V3<T> t = vzero<T>();
 PPR_UNROLL
@@ -213,12 +227,12 @@ PPR_UNROLL
             V3<T> aw = qrot(qw, ax[k]);
             T qd = dot(aw, w_err);
             T sc = c.ke[k] * (ang[k] - c.target[k]) + c.kd[k] * qd + c.act[k] -
-                   joint_limit_force(ang[k], qd, c.lo[k], c.hi[k], c.lke[k], c.lkd[k]);
+                   (LIMITS ? joint_limit_force(ang[k], qd, c.lo[k], c.hi[k], c.lke[k], c.lkd[k]) : T(0));
             t += aw * sc;
         }
         t_out = clamp3(t, T(1e4));
         f_out = clamp3(x_err * ake + v_err * akd, T(1e4));
-    } else if (js.type == JT_FIXED) {
+    } else if (JM == JM_ALL && js.type == JT_FIXED) {
         V3<T> e = qvec(r_err);
         T l = sqrt(dot(e, e));
         T inv = l > T(0) ? T(1) / l : T(0);
@@ -230,7 +244,7 @@ PPR_UNROLL
 
 // Reverse of joint_fwd + the wrench scatter.  adjFp / adjFc = adjoints of the parent's / child's total wrench.
 // Accumulates into adjP / adj_xcp (parent state, parent world-COM), adjC / adj_xcc and the per-dof parameter adjoints.
-template <class T>
+template <class T, int JM = JM_ALL, bool LIMITS = true, bool QOFF = true>
 PPR_HD void joint_adj(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T akd, const Body<T>& P, V3<T> xcp,
                       bool has_parent, const Body<T>& C, V3<T> xcc, const Wrench<T>& adjFp, const Wrench<T>& adjFc,
                       Body<T>& adjP, V3<T>& adj_xcp, Body<T>& adjC, V3<T>& adj_xcc, T* adj_target, T* adj_act,
@@ -257,12 +271,12 @@ PPR_HD void joint_adj(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
     V3<T> gt = gtp - adjFc.t;
     // forward values of t, f are needed for the arm adjoints and clamp masks -> computed per type below
 
-    if (js.type == JT_REVOLUTE) {
+    if (JM != JM_COMPOUND && js.type == JT_REVOLUTE) {
         V3<T> axis_p = qrot(qA, js.axis), axis_c = qrot(C.r, js.axis);
         T q = revolute_angle(js.axis, r_err);
         T qd = dot(w_err, axis_p);
         T sc = c.ke[0] * (q - c.target[0]) + c.kd[0] * qd + c.act[0] -
-               joint_limit_force(q, qd, c.lo[0], c.hi[0], c.lke[0], c.lkd[0]);
+               (LIMITS ? joint_limit_force(q, qd, c.lo[0], c.hi[0], c.lke[0], c.lkd[0]) : T(0));
         f_out = x_err * ake + v_err * akd;
         V3<T> gf = gfp - adjFc.f + cross(gtp, arm_p) - cross(adjFc.t, arm_c);
         V3<T> g_armp = cross(f_out, gtp), g_armc = -cross(f_out, adjFc.t);
@@ -275,7 +289,7 @@ PPR_HD void joint_adj(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
         g_werr += gt * c2;
         T g_qd = -c2 * dot(gt, axis_p);
         T g_q = T(0);
-        joint_scalar_adj(q, qd, c, 0, g_sc, g_q, g_qd, adj_target, adj_act, adj_ke, adj_kd);
+        joint_scalar_adj<T, LIMITS>(q, qd, c, 0, g_sc, g_q, g_qd, adj_target, adj_act, adj_ke, adj_kd);
         g_werr += axis_p * g_qd;
         g_axp += w_err * g_qd;
         revolute_angle_adj(js.axis, r_err, g_q, g_rerr);
@@ -297,9 +311,8 @@ PPR_HD void joint_adj(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
         adjP.r += qmul(g_qA, qconj(js.qpj));
         return;
     }
-    if (js.type == JT_COMPOUND) {
-        Q4<T> tmp = qmul(qconj(js.qoff), r_err);
-        Q4<T> q_pc = qmul(tmp, js.qoff);
+    if (JM != JM_REVOLUTE && js.type == JT_COMPOUND) {
+        Q4<T> q_pc = QOFF ? qmul(qmul(qconj(js.qoff), r_err), js.qoff) : r_err;
         const V3<T> ex = v3<T>(T(1), T(0), T(0)), ey = v3<T>(T(0), T(1), T(0)), ez = v3<T>(T(0), T(0), T(1));
         V3<T> c0 = qrot(q_pc, ex), c1 = qrot(q_pc, ey), c2v = qrot(q_pc, ez);
         T ang[3] = {-atan2(c2v.y, c2v.z), -safe_asin(-c2v.x), -atan2(c1.x, c0.x)};
@@ -308,7 +321,7 @@ PPR_HD void joint_adj(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
         Q4<T> q1 = q_axis_angle(a1, ang[1]);
         Q4<T> q10 = qmul(q1, q0);
         V3<T> a2 = qrot(q10, ez);
-        Q4<T> qw = qmul(qA, js.qoff);
+        Q4<T> qw = QOFF ? qmul(qA, js.qoff) : qA;
         V3<T> ax[3] = {ex, a1, a2};
         V3<T> aw[3];
         T qd[3], sc[3];
@@ -318,7 +331,7 @@ PPR_UNROLL
             aw[k] = qrot(qw, ax[k]);
             qd[k] = dot(aw[k], w_err);
             sc[k] = c.ke[k] * (ang[k] - c.target[k]) + c.kd[k] * qd[k] + c.act[k] -
-                    joint_limit_force(ang[k], qd[k], c.lo[k], c.hi[k], c.lke[k], c.lkd[k]);
+                    (LIMITS ? joint_limit_force(ang[k], qd[k], c.lo[k], c.hi[k], c.lke[k], c.lkd[k]) : T(0));
             traw += aw[k] * sc[k];
         }
         V3<T> fraw = x_err * ake + v_err * akd;
@@ -337,7 +350,7 @@ PPR_UNROLL
             T g_sc = dot(gtr, aw[k]);
             V3<T> g_aw = gtr * sc[k];
             T g_qd = T(0);
-            joint_scalar_adj(ang[k], qd[k], c, k, g_sc, g_ang[k], g_qd, adj_target, adj_act, adj_ke, adj_kd);
+            joint_scalar_adj<T, LIMITS>(ang[k], qd[k], c, k, g_sc, g_ang[k], g_qd, adj_target, adj_act, adj_ke, adj_kd);
             g_aw += w_err * g_qd;
             g_werr += aw[k] * g_qd;
             g_qw += qrot_adj_q(qw, ax[k], g_aw);
@@ -360,11 +373,14 @@ PPR_UNROLL
         den = c1.x * c1.x + c0.x * c0.x;
         if (den > T(0)) { g_c1.x += g_psi * c0.x / den; g_c0.x -= g_psi * c1.x / den; }
         Q4<T> g_qpc = qrot_adj_q(q_pc, ex, g_c0) + qrot_adj_q(q_pc, ey, g_c1) + qrot_adj_q(q_pc, ez, g_c2);
-        // q_pc = tmp * qoff ; tmp = conj(qoff) * r_err
-        Q4<T> g_tmp = qmul(g_qpc, qconj(js.qoff));
-        g_rerr += qmul(js.qoff, g_tmp);
-        // qw = qA * qoff
-        g_qA += qmul(g_qw, qconj(js.qoff));
+        // q_pc = (conj(qoff) * r_err) * qoff ; qw = qA * qoff
+        if (QOFF) {
+            g_rerr += qmul(js.qoff, qmul(g_qpc, qconj(js.qoff)));
+            g_qA += qmul(g_qw, qconj(js.qoff));
+        } else {
+            g_rerr += g_qpc;
+            g_qA += g_qw;
+        }
         adjC.x += g_armc; adj_xcc -= g_armc;
         if (has_parent) { adj_xcp -= g_armp; }
         V3<T> g_xA = g_armp - g_xerr;
@@ -379,7 +395,7 @@ PPR_UNROLL
         adjP.r += qmul(g_qA, qconj(js.qpj));
         return;
     }
-    if (js.type == JT_FIXED) {
+    if (JM == JM_ALL && js.type == JT_FIXED) {
         V3<T> e = qvec(r_err);
         T l = sqrt(dot(e, e));
         T inv = l > T(0) ? T(1) / l : T(0);
@@ -491,7 +507,7 @@ PPR_HD void integrate_adj(const Body<T>& b, V3<T> xc, V3<T> com, const Wrench<T>
 // ------------------------------------------------------------------------------------------ FK (K1)
 // P = parent world pose / twist (identity, zero when the joint has no parent). jq / jqd point at this joint's
 // coordinates / dofs.
-template <class T>
+template <class T, int JM = JM_ALL>
 PPR_HD Body<T> fk_joint_fwd(const JointStatic<T>& js, V3<T> com, const Body<T>& P, const T* jq, const T* jqd) {
     V3<T> x_wj = P.x + qrot(P.r, js.xpj);
     Q4<T> r_wj = qmul(P.r, js.qpj);
@@ -502,10 +518,10 @@ PPR_HD Body<T> fk_joint_fwd(const JointStatic<T>& js, V3<T> com, const Body<T>& 
         r_jc = q4<T>(jq[3], jq[4], jq[5], jq[6]);
         w_j = v3<T>(jqd[0], jqd[1], jqd[2]);
         v_j = v3<T>(jqd[3], jqd[4], jqd[5]);
-    } else if (js.type == JT_REVOLUTE) {
+    } else if (JM != JM_COMPOUND && js.type == JT_REVOLUTE) {
         r_jc = q_axis_angle(js.axis, jq[0]);
         w_j = js.axis * jqd[0];
-    } else if (js.type == JT_COMPOUND) {
+    } else if (JM != JM_REVOLUTE && js.type == JT_COMPOUND) {
         const V3<T> ex = v3<T>(T(1), T(0), T(0)), ey = v3<T>(T(0), T(1), T(0)), ez = v3<T>(T(0), T(0), T(1));
         Q4<T> q0 = q_axis_angle(ex, jq[0]);
         V3<T> a1 = qrot(q0, ey);
@@ -525,7 +541,7 @@ PPR_HD Body<T> fk_joint_fwd(const JointStatic<T>& js, V3<T> com, const Body<T>& 
     return o;
 }
 
-template <class T>
+template <class T, int JM = JM_ALL>
 PPR_HD void fk_joint_adj(const JointStatic<T>& js, V3<T> com, const Body<T>& P, const T* jq, const T* jqd,
                          const Body<T>& adjO, Body<T>& adjP, T* adj_jq, T* adj_jqd) {
     Q4<T> r_wj = qmul(P.r, js.qpj);
@@ -547,7 +563,7 @@ PPR_HD void fk_joint_adj(const JointStatic<T>& js, V3<T> com, const Body<T>& P, 
         adj_jq[3] += g_rjc.x; adj_jq[4] += g_rjc.y; adj_jq[5] += g_rjc.z; adj_jq[6] += g_rjc.w;
         adj_jqd[0] += g_wj.x; adj_jqd[1] += g_wj.y; adj_jqd[2] += g_wj.z;
         adj_jqd[3] += g_vj.x; adj_jqd[4] += g_vj.y; adj_jqd[5] += g_vj.z;
-    } else if (js.type == JT_REVOLUTE) {
+    } else if (JM != JM_COMPOUND && js.type == JT_REVOLUTE) {
         Q4<T> r_jc = q_axis_angle(js.axis, jq[0]);
         V3<T> w_j = js.axis * jqd[0];
         g_rwj += qrot_adj_q(r_wj, w_j, g_ww);
@@ -556,7 +572,7 @@ PPR_HD void fk_joint_adj(const JointStatic<T>& js, V3<T> com, const Body<T>& P, 
         V3<T> dummy = vzero<T>();
         adj_jq[0] += q_axis_angle_adj(js.axis, jq[0], g_rjc, dummy);
         adj_jqd[0] += dot(js.axis, g_wj);
-    } else if (js.type == JT_COMPOUND) {
+    } else if (JM != JM_REVOLUTE && js.type == JT_COMPOUND) {
         const V3<T> ex = v3<T>(T(1), T(0), T(0)), ey = v3<T>(T(0), T(1), T(0)), ez = v3<T>(T(0), T(0), T(1));
         Q4<T> q0 = q_axis_angle(ex, jq[0]);
         V3<T> a1 = qrot(q0, ey);

@@ -30,6 +30,9 @@ typedef Wrench<float> WrenchF;
 #define PPR_MAX_CHILD 8
 #define PPR_CKPT_FLOATS 19  // body_q 7 + body_qd 6 + total wrench 6
 #define PPR_BLOCK 128
+#define PPR_WARPS (PPR_BLOCK / 32)
+#define PPR_CLIST_CAP 16  // penetrating points listed per body before falling back to the cooperative path
+#define PPR_CLIST_STRIDE (PPR_CLIST_CAP + 1)
 #define FULL 0xffffffffu
 
 static std::atomic<int64_t> g_launches{0};
@@ -50,6 +53,7 @@ struct DevModel {
     const float4* mats;       // [nshape] ke kd kf mu
     const float* aabb;        // [nb,8] lo xyz, hi xyz, max dist, pad
     float g[3], ake, akd;
+    int mat_uniform;          // every contact uses material row cmat[0]
 };
 
 struct ppr_model {
@@ -59,6 +63,7 @@ struct ppr_model {
     void* blob;               // one device allocation holding every array
     size_t xpj_offset;        // byte offset of xpj inside blob
     std::vector<float> h_xpj;
+    int variant;              // 0: FREE+REVOLUTE, 1: FREE+COMPOUND (both: no limits, identity q_off), 2: generic
 };
 #define PPR_MAGIC 0x50505231u
 
@@ -123,35 +128,80 @@ __device__ __forceinline__ LaneInfo lane_setup(const DevModel& M, int64_t warp, 
     return L;
 }
 
-// lowest possible world-y of any contact point of this body (exact bound on the body-frame AABB; quat_rotate
-// is linear in the point even for non-unit quaternions)
-__device__ __forceinline__ bool contact_possible(const LaneInfo& L, const BodyF& s) {
-    float w = s.r.w, ux = s.r.x, uy = s.r.y, uz = s.r.z;
-    float m0 = 2.f * (w * uz + uy * ux), m1 = 2.f * w * w - 1.f + 2.f * uy * uy, m2 = 2.f * (uy * uz - w * ux);
-    float ylow = s.x.y + fminf(m0 * L.aabb[0], m0 * L.aabb[3]) + fminf(m1 * L.aabb[1], m1 * L.aabb[4]) +
-                 fminf(m2 * L.aabb[2], m2 * L.aabb[5]) - L.aabb[6];
-    return L.valid && (L.c1 > L.c0) && !(ylow > 1e-6f);
-}
-
 __device__ __forceinline__ ContactMat<float> load_mat(const DevModel& M, int k) {
     float4 m = M.mats[M.cmat[k]];
     ContactMat<float> c; c.ke = m.x; c.kd = m.y; c.kf = m.z; c.mu = m.w;
     return c;
 }
+__device__ __forceinline__ ContactMat<float> mat_of(const DevModel& M, const ContactMat<float>& cm0, int k) {
+    return M.mat_uniform ? cm0 : load_mat(M, k);
+}
+
+// Phase A of K3 / K3^T: which contact points of which bodies can penetrate the ground plane.
+//   small bodies (<= big_threshold points, e.g. the 8 box corners of human / quad): the owning lane will just
+//     loop over its own points -> returns -2
+//   big bodies (laikago's collision meshes, 96..596 vertices): the WHOLE WARP tests the body's points (only the
+//     y-row of the rotation and the height are broadcast: 6 shuffles) and the penetrating point indices are
+//     compacted into the owner lane's list in shared memory -> returns their count, or -1 if more than
+//     PPR_CLIST_CAP penetrate (owner falls back to the cooperative evaluate-and-reduce path).
+// The test uses a 1e-6 m margin; the exact `c > 0` rejection of the reference is re-applied per point in phase B.
+__device__ __forceinline__ int contact_candidates(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
+                                                  int* __restrict__ clist) {
+    float w = s.r.w, ux = s.r.x, uy = s.r.y, uz = s.r.z;
+    float m0 = 2.f * (w * uz + uy * ux), m1 = 2.f * w * w - 1.f + 2.f * uy * uy, m2 = 2.f * (uy * uz - w * ux);
+    float ylow = s.x.y + fminf(m0 * L.aabb[0], m0 * L.aabb[3]) + fminf(m1 * L.aabb[1], m1 * L.aabb[4]) +
+                 fminf(m2 * L.aabb[2], m2 * L.aabb[5]) - L.aabb[6];
+    bool maybe = L.valid && (L.c1 > L.c0) && !(ylow > 1e-6f);
+    bool big = (L.c1 - L.c0) > M.big_threshold;
+    int mine = (maybe && !big) ? -2 : 0;
+    unsigned mask = __ballot_sync(FULL, maybe && big);
+    if (mask == 0) return mine;
+    const unsigned lt = (1u << lane) - 1u;
+    while (mask) {
+        int a = __ffs(mask) - 1;
+        mask &= mask - 1;
+        float a0 = shf(m0, a), a1 = shf(m1, a), a2 = shf(m2, a), ay = shf(s.x.y, a);
+        int c0 = __shfl_sync(FULL, L.c0, a), c1 = __shfl_sync(FULL, L.c1, a);
+        int cnt = 0;
+        for (int base = c0; base < c1; base += 32) {
+            int k = base + lane;
+            bool pen = false;
+            if (k < c1) {
+                float4 p = M.cpt[k];
+                float c = ay + a0 * p.x + a1 * p.y + a2 * p.z - p.w;
+                pen = !(c > 1e-6f);
+            }
+            unsigned bits = __ballot_sync(FULL, pen);
+            if (pen) {
+                int pos = cnt + __popc(bits & lt);
+                if (pos < PPR_CLIST_CAP) clist[a * PPR_CLIST_STRIDE + pos] = k;
+            }
+            cnt += __popc(bits);
+        }
+        if (lane == a) mine = cnt > PPR_CLIST_CAP ? -1 : cnt;
+    }
+    __syncwarp();
+    return mine;
+}
 
 // K3 for the whole warp: subtracts contact wrenches from F (per lane = per body)
 __device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
-                                                  WrenchF& F) {
-    bool maybe = contact_possible(L, s);
-    bool big = (L.c1 - L.c0) > M.big_threshold;
-    if (maybe && !big) {
+                                                  const ContactMat<float>& cm0, int* __restrict__ clist, WrenchF& F) {
+    int cand = contact_candidates(M, L, lane, s, clist);
+    if (cand == -2) {
         for (int k = L.c0; k < L.c1; ++k) {
             float4 p = M.cpt[k];
-            contact_point_fwd(s, xc, v3<float>(p.x, p.y, p.z), p.w, load_mat(M, k), F);
+            contact_point_fwd(s, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), F);
+        }
+    } else {
+        for (int i = 0; i < cand; ++i) {
+            int k = clist[lane * PPR_CLIST_STRIDE + i];
+            float4 p = M.cpt[k];
+            contact_point_fwd(s, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), F);
         }
     }
-    unsigned mask = __ballot_sync(FULL, maybe && big);
-    while (mask) {
+    unsigned mask = __ballot_sync(FULL, cand == -1);
+    while (mask) {  // many penetrating points: evaluate cooperatively and reduce
         int a = __ffs(mask) - 1;
         mask &= mask - 1;
         BodyF sa = shf_body(s, a);
@@ -160,26 +210,33 @@ __device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneI
         WrenchF W = wrench_zero<float>();
         for (int k = c0 + lane; k < c1; k += 32) {
             float4 p = M.cpt[k];
-            contact_point_fwd(sa, xca, v3<float>(p.x, p.y, p.z), p.w, load_mat(M, k), W);
+            contact_point_fwd(sa, xca, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), W);
         }
         W.t.x = warp_sum(W.t.x); W.t.y = warp_sum(W.t.y); W.t.z = warp_sum(W.t.z);
         W.f.x = warp_sum(W.f.x); W.f.y = warp_sum(W.f.y); W.f.z = warp_sum(W.f.z);
         if (lane == a) { F.t += W.t; F.f += W.f; }
     }
+    __syncwarp();  // clist is reused by the next substep
 }
 
 // K3^T for the whole warp
 __device__ __forceinline__ void warp_contacts_adj(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
+                                                  const ContactMat<float>& cm0, int* __restrict__ clist,
                                                   const WrenchF& adjF, BodyF& adjS, F3& adj_xc) {
-    bool maybe = contact_possible(L, s);
-    bool big = (L.c1 - L.c0) > M.big_threshold;
-    if (maybe && !big) {
+    int cand = contact_candidates(M, L, lane, s, clist);
+    if (cand == -2) {
         for (int k = L.c0; k < L.c1; ++k) {
             float4 p = M.cpt[k];
-            contact_point_adj(s, xc, v3<float>(p.x, p.y, p.z), p.w, load_mat(M, k), adjF, adjS, adj_xc);
+            contact_point_adj(s, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), adjF, adjS, adj_xc);
+        }
+    } else {
+        for (int i = 0; i < cand; ++i) {
+            int k = clist[lane * PPR_CLIST_STRIDE + i];
+            float4 p = M.cpt[k];
+            contact_point_adj(s, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), adjF, adjS, adj_xc);
         }
     }
-    unsigned mask = __ballot_sync(FULL, maybe && big);
+    unsigned mask = __ballot_sync(FULL, cand == -1);
     while (mask) {
         int a = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -191,7 +248,7 @@ __device__ __forceinline__ void warp_contacts_adj(const DevModel& M, const LaneI
         F3 Axc = vzero<float>();
         for (int k = c0 + lane; k < c1; k += 32) {
             float4 p = M.cpt[k];
-            contact_point_adj(sa, xca, v3<float>(p.x, p.y, p.z), p.w, load_mat(M, k), aFa, A, Axc);
+            contact_point_adj(sa, xca, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), aFa, A, Axc);
         }
         A.x.x = warp_sum(A.x.x); A.x.y = warp_sum(A.x.y); A.x.z = warp_sum(A.x.z);
         A.r.x = warp_sum(A.r.x); A.r.y = warp_sum(A.r.y); A.r.z = warp_sum(A.r.z); A.r.w = warp_sum(A.r.w);
@@ -200,15 +257,17 @@ __device__ __forceinline__ void warp_contacts_adj(const DevModel& M, const LaneI
         Axc.x = warp_sum(Axc.x); Axc.y = warp_sum(Axc.y); Axc.z = warp_sum(Axc.z);
         if (lane == a) { body_acc(adjS, A); adj_xc += Axc; }
     }
+    __syncwarp();
 }
 
 // articulation FK across the warp, level by level (parents before children)
+template <int JM>
 __device__ __forceinline__ BodyF warp_fk(const DevModel& M, const LaneInfo& L, const float* jq, const float* jqd) {
     BodyF s = body_identity<float>();
     for (int d = 0; d <= M.maxdepth; ++d) {
         BodyF P = shf_body(s, L.parent_lane);
         if (!L.has_parent) P = body_identity<float>();
-        if (L.depth == d) s = fk_joint_fwd(L.js, L.com, P, jq, jqd);
+        if (L.depth == d) s = fk_joint_fwd<float, JM>(L.js, L.com, P, jq, jqd);
     }
     return s;
 }
@@ -235,6 +294,7 @@ __device__ __forceinline__ void load_joint_coords(const LaneInfo& L, const float
 }
 
 // ----------------------------------------------------------------------------------------------- FK kernels
+template <int JM>
 __global__ void __launch_bounds__(PPR_BLOCK)
 fk_forward_kernel(DevModel M, int64_t n, const float* __restrict__ q, const float* __restrict__ qd,
                   float* __restrict__ body_q, float* __restrict__ body_qd) {
@@ -244,7 +304,7 @@ fk_forward_kernel(DevModel M, int64_t n, const float* __restrict__ q, const floa
     LaneInfo L = lane_setup(M, warp, lane, n);
     float jq[7], jqd[6];
     load_joint_coords(L, q, qd, M.nq, M.nqd, jq, jqd);
-    BodyF s = warp_fk(M, L, jq, jqd);
+    BodyF s = warp_fk<JM>(M, L, jq, jqd);
     if (L.valid) {
         float* o = body_q + ((int64_t)L.env * M.nb + L.body) * 7;
         o[0] = s.x.x; o[1] = s.x.y; o[2] = s.x.z; o[3] = s.r.x; o[4] = s.r.y; o[5] = s.r.z; o[6] = s.r.w;
@@ -254,6 +314,7 @@ fk_forward_kernel(DevModel M, int64_t n, const float* __restrict__ q, const floa
 }
 
 // shared by fk_backward_kernel and the tail of rollout_backward_kernel
+template <int JM>
 __device__ __forceinline__ void warp_fk_adjoint(const DevModel& M, const LaneInfo& L, const BodyF& s, BodyF adj,
                                                 const float* jq, const float* jqd, float* __restrict__ adj_q,
                                                 float* __restrict__ adj_qd) {
@@ -262,7 +323,7 @@ __device__ __forceinline__ void warp_fk_adjoint(const DevModel& M, const LaneInf
         BodyF P = shf_body(s, L.parent_lane);
         if (!L.has_parent) P = body_identity<float>();
         BodyF adjP = body_zero<float>();
-        if (L.depth == d) fk_joint_adj(L.js, L.com, P, jq, jqd, adj, adjP, ajq, ajqd);
+        if (L.depth == d) fk_joint_adj<float, JM>(L.js, L.com, P, jq, jqd, adj, adjP, ajq, ajqd);
         gather_children_body(M, L, adjP, adj);
     }
     if (L.valid) {
@@ -274,6 +335,7 @@ __device__ __forceinline__ void warp_fk_adjoint(const DevModel& M, const LaneInf
     }
 }
 
+template <int JM>
 __global__ void __launch_bounds__(PPR_BLOCK)
 fk_backward_kernel(DevModel M, int64_t n, const float* __restrict__ q, const float* __restrict__ qd,
                    const float* __restrict__ adj_body_q, const float* __restrict__ adj_body_qd,
@@ -284,7 +346,7 @@ fk_backward_kernel(DevModel M, int64_t n, const float* __restrict__ q, const flo
     LaneInfo L = lane_setup(M, warp, lane, n);
     float jq[7], jqd[6];
     load_joint_coords(L, q, qd, M.nq, M.nqd, jq, jqd);
-    BodyF s = warp_fk(M, L, jq, jqd);
+    BodyF s = warp_fk<JM>(M, L, jq, jqd);
     BodyF adj = body_zero<float>();
     if (L.valid) {
         const float* a = adj_body_q + ((int64_t)L.env * M.nb + L.body) * 7;
@@ -292,7 +354,7 @@ fk_backward_kernel(DevModel M, int64_t n, const float* __restrict__ q, const flo
         adj.x = v3<float>(a[0], a[1], a[2]); adj.r = q4<float>(a[3], a[4], a[5], a[6]);
         adj.w = v3<float>(b[0], b[1], b[2]); adj.v = v3<float>(b[3], b[4], b[5]);
     }
-    warp_fk_adjoint(M, L, s, adj, jq, jqd, adj_q, adj_qd);
+    warp_fk_adjoint<JM>(M, L, s, adj, jq, jqd, adj_q, adj_qd);
 }
 
 // ----------------------------------------------------------------------------------------------- rollout
@@ -326,15 +388,16 @@ __device__ __forceinline__ void store_wrench_row(float* base, const WrenchF& w) 
 }
 
 // forces of one substep; F = total wrench on this lane's body. Optionally exports the grf / jaf side channels.
+template <int JM, bool LIMITS, bool QOFF>
 __device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
-                                            const JointCtl<float>& ctl, const float* res_f_row, float* grf_row,
-                                            float* jaf_row, WrenchF& F) {
+                                            const JointCtl<float>& ctl, const ContactMat<float>& cm0, int* clist,
+                                            const float* res_f_row, float* grf_row, float* jaf_row, WrenchF& F) {
     F = wrench_zero<float>();
     if (res_f_row && L.valid) {
         F.t = v3<float>(res_f_row[0], res_f_row[1], res_f_row[2]);
         F.f = v3<float>(res_f_row[3], res_f_row[4], res_f_row[5]);
     }
-    warp_contacts_fwd(M, L, lane, s, xc, F);
+    warp_contacts_fwd(M, L, lane, s, xc, cm0, clist, F);
     WrenchF G = F;
     if (grf_row && L.valid) store_wrench_row(grf_row, F);
     // joints: this lane is the child of its joint
@@ -342,7 +405,7 @@ __device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L
     F3 xcp = shf3(xc, L.parent_lane);
     if (!L.has_parent) { P = body_identity<float>(); xcp = vzero<float>(); }
     F3 t, f, ap, ac;
-    joint_fwd(L.js, ctl, M.ake, M.akd, P, xcp, L.has_parent, s, xc, t, f, ap, ac);
+    joint_fwd<float, JM, LIMITS, QOFF>(L.js, ctl, M.ake, M.akd, P, xcp, L.has_parent, s, xc, t, f, ap, ac);
     WrenchF Wp = wrench_zero<float>();
     if (L.type != JT_FREE) {
         F.t -= t + cross(ac, f); F.f -= f;
@@ -362,11 +425,22 @@ __device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L
     }
 }
 
-__global__ void __launch_bounds__(PPR_BLOCK)
+#ifndef PPR_FWD_MINB
+#define PPR_FWD_MINB 1
+#endif
+#ifndef PPR_BWD_MINB
+#define PPR_BWD_MINB 1
+#endif
+template <int JM, bool LIMITS, bool QOFF>
+__global__ void __launch_bounds__(PPR_BLOCK, PPR_FWD_MINB)
 rollout_forward_kernel(DevModel M, RolloutArgs A) {
+    __shared__ int clist_all[PPR_WARPS * 32 * PPR_CLIST_STRIDE];
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
+    int* clist = clist_all + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
     if (warp >= A.nwarps) return;
+    ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
+    if (M.nc > 0) cm0 = load_mat(M, 0);
     LaneInfo L = lane_setup(M, warp, lane, A.bs);
     // per-env parameters of this body / joint
     int64_t eb = (int64_t)L.env * M.nb + L.body;
@@ -387,7 +461,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     F3 g = v3<float>(M.g[0], M.g[1], M.g[2]);
     float jq[7], jqd[6];
     load_joint_coords(L, A.q_init, A.qd_init, M.nq, M.nqd, jq, jqd);
-    BodyF s = warp_fk(M, L, jq, jqd);
+    BodyF s = warp_fk<JM>(M, L, jq, jqd);
 
     float* ck = A.ckpt + (warp * PPR_CKPT_FLOATS) * 32 + lane;
     const int64_t ck_step = A.nwarps * PPR_CKPT_FLOATS * 32;
@@ -407,7 +481,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         F3 xc = s.x + qrot(s.r, L.com);
         load_ctl(M, L, A, t, ke, kd, ctl);
         WrenchF F;
-        warp_forces(M, L, lane, s, xc, ctl, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
+        warp_forces<JM, LIMITS, QOFF>(M, L, lane, s, xc, ctl, cm0, clist, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
                     (frame && A.out_grf) ? A.out_grf + frow * 6 : nullptr,
                     (frame && A.out_jaf) ? A.out_jaf + frow * 6 : nullptr, F);
         // checkpoint (coalesced: component-major rows of 32 lanes)
@@ -422,11 +496,16 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     }
 }
 
-__global__ void __launch_bounds__(PPR_BLOCK)
+template <int JM, bool LIMITS, bool QOFF>
+__global__ void __launch_bounds__(PPR_BLOCK, PPR_BWD_MINB)
 rollout_backward_kernel(DevModel M, RolloutArgs A) {
+    __shared__ int clist_all[PPR_WARPS * 32 * PPR_CLIST_STRIDE];
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
+    int* clist = clist_all + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
     if (warp >= A.nwarps) return;
+    ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
+    if (M.nc > 0) cm0 = load_mat(M, 0);
     LaneInfo L = lane_setup(M, warp, lane, A.bs);
     int64_t eb = (int64_t)L.env * M.nb + L.body;
     float inv_m = A.inv_m[eb];
@@ -507,8 +586,8 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         BodyF adjP = body_zero<float>();
         F3 adj_xcp = vzero<float>();
         float g_target[3] = {0, 0, 0}, g_act[3] = {0, 0, 0};
-        joint_adj(L.js, ctl, M.ake, M.akd, P, xcp, L.has_parent, s, xc, adjFp, adjF, adjP, adj_xcp, adjS, adj_xc,
-                  g_target, g_act, a_ke, a_kd);
+        joint_adj<float, JM, LIMITS, QOFF>(L.js, ctl, M.ake, M.akd, P, xcp, L.has_parent, s, xc, adjFp, adjF, adjP,
+                                           adj_xcp, adjS, adj_xc, g_target, g_act, a_ke, a_kd);
         adjP.x += adj_xcp;
         adjP.r += qrot_adj_q(P.r, com_par, adj_xcp);
         if (!L.has_parent) adjP = body_zero<float>();
@@ -526,7 +605,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
             }
         }
         // K3^T
-        warp_contacts_adj(M, L, lane, s, xc, adjF, adjS, adj_xc);
+        warp_contacts_adj(M, L, lane, s, xc, cm0, clist, adjF, adjS, adj_xc);
         // K2^T
         if (A.adj_res_f && L.valid) store_wrench_row(A.adj_res_f + ((tp * A.bs + L.env) * M.nb + L.body) * 6, adjF);
         // world COM -> pose
@@ -538,8 +617,8 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     {
         float jq[7], jqd[6];
         load_joint_coords(L, A.q_init, A.qd_init, M.nq, M.nqd, jq, jqd);
-        BodyF s0 = warp_fk(M, L, jq, jqd);
-        warp_fk_adjoint(M, L, s0, adjN, jq, jqd, A.adj_q_init, A.adj_qd_init);
+        BodyF s0 = warp_fk<JM>(M, L, jq, jqd);
+        warp_fk_adjoint<JM>(M, L, s0, adjN, jq, jqd, A.adj_q_init, A.adj_qd_init);
     }
     if (L.valid) {
         A.adj_inv_m[eb] = a_inv_m;
@@ -663,6 +742,24 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
     d.mats = (const float4*)(base + o_mats); d.aabb = (const float*)(base + o_aabb);
     d.g[0] = D->gravity[0]; d.g[1] = D->gravity[1]; d.g[2] = D->gravity[2];
     d.ake = D->joint_attach_ke; d.akd = D->joint_attach_kd;
+    d.mat_uniform = 1;
+    for (size_t k = 1; k < cmat.size(); ++k) if (cmat[k] != cmat[0]) d.mat_uniform = 0;
+    bool any_rev = false, any_cmp = false, any_other = false, limits = false, qoffs = false;
+    for (int i = 0; i < nb; ++i) {
+        int ty = D->joint_type[i];
+        if (ty == JT_REVOLUTE) any_rev = true;
+        else if (ty == JT_COMPOUND) {
+            any_cmp = true;
+            const float* q = D->joint_X_c + 7 * i + 3;
+            if (q[0] != 0.f || q[1] != 0.f || q[2] != 0.f || q[3] != 1.f) qoffs = true;
+        } else if (ty != JT_FREE) any_other = true;
+    }
+    for (int k = 0; k < D->nqd; ++k) if (D->joint_limit_ke[k] != 0.f || D->joint_limit_kd[k] != 0.f) limits = true;
+    m->variant = 2;
+    if (!any_other && !limits && !qoffs) {
+        if (!any_cmp) m->variant = 0;
+        else if (!any_rev) m->variant = 1;
+    }
     m->xpj_offset = o_xpj;
     m->h_xpj.assign(D->joint_X_p, D->joint_X_p + nb * 7);
     m->magic = PPR_MAGIC;
@@ -707,7 +804,11 @@ extern "C" int ppr_fk_forward(ppr_model_t m, int64_t n, const float* q, const fl
     if (!check(m)) return PPR_E_HANDLE;
     if (n < 0 || !q || !qd || !bq || !bqd) return PPR_E_ARG;
     if (n == 0) return 0;
-    fk_forward_kernel<<<grid_for(nwarps_for(m->d, n)), PPR_BLOCK, 0, (cudaStream_t)stream>>>(m->d, n, q, qd, bq, bqd);
+    dim3 grid(grid_for(nwarps_for(m->d, n)));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->variant == 0) fk_forward_kernel<JM_REVOLUTE><<<grid, PPR_BLOCK, 0, st>>>(m->d, n, q, qd, bq, bqd);
+    else if (m->variant == 1) fk_forward_kernel<JM_COMPOUND><<<grid, PPR_BLOCK, 0, st>>>(m->d, n, q, qd, bq, bqd);
+    else fk_forward_kernel<JM_ALL><<<grid, PPR_BLOCK, 0, st>>>(m->d, n, q, qd, bq, bqd);
     g_launches++;
     return (int)cudaGetLastError();
 }
@@ -717,8 +818,11 @@ extern "C" int ppr_fk_backward(ppr_model_t m, int64_t n, const float* q, const f
     if (!check(m)) return PPR_E_HANDLE;
     if (n < 0 || !q || !qd || !abq || !abqd || !aq || !aqd) return PPR_E_ARG;
     if (n == 0) return 0;
-    fk_backward_kernel<<<grid_for(nwarps_for(m->d, n)), PPR_BLOCK, 0, (cudaStream_t)stream>>>(m->d, n, q, qd, abq, abqd,
-                                                                                                 aq, aqd);
+    dim3 grid(grid_for(nwarps_for(m->d, n)));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->variant == 0) fk_backward_kernel<JM_REVOLUTE><<<grid, PPR_BLOCK, 0, st>>>(m->d, n, q, qd, abq, abqd, aq, aqd);
+    else if (m->variant == 1) fk_backward_kernel<JM_COMPOUND><<<grid, PPR_BLOCK, 0, st>>>(m->d, n, q, qd, abq, abqd, aq, aqd);
+    else fk_backward_kernel<JM_ALL><<<grid, PPR_BLOCK, 0, st>>>(m->d, n, q, qd, abq, abqd, aq, aqd);
     g_launches++;
     return (int)cudaGetLastError();
 }
@@ -745,7 +849,11 @@ extern "C" int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, in
     A.q_init = q_init; A.qd_init = qd_init; A.torques = torques; A.res_f = res_f; A.refs = refs; A.ke = ke; A.kd = kd;
     A.inv_m = inv_m; A.I = I; A.inv_I = inv_I;
     A.out_pos = out_pos; A.out_vel = out_vel; A.out_grf = out_grf; A.out_jaf = out_jaf; A.ckpt = (float*)ws;
-    rollout_forward_kernel<<<grid_for(A.nwarps), PPR_BLOCK, 0, (cudaStream_t)stream>>>(m->d, A);
+    dim3 grid(grid_for(A.nwarps));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->variant == 0) rollout_forward_kernel<JM_REVOLUTE, false, false><<<grid, PPR_BLOCK, 0, st>>>(m->d, A);
+    else if (m->variant == 1) rollout_forward_kernel<JM_COMPOUND, false, false><<<grid, PPR_BLOCK, 0, st>>>(m->d, A);
+    else rollout_forward_kernel<JM_ALL, true, true><<<grid, PPR_BLOCK, 0, st>>>(m->d, A);
     g_launches++;
     return (int)cudaGetLastError();
 }
@@ -772,7 +880,11 @@ extern "C" int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, i
     A.adj_pos = adj_pos; A.adj_vel = adj_vel; A.adj_q_init = adj_q_init; A.adj_qd_init = adj_qd_init;
     A.adj_torques = adj_torques; A.adj_res_f = adj_res_f; A.adj_refs = adj_refs; A.adj_ke = adj_ke; A.adj_kd = adj_kd;
     A.adj_inv_m = adj_inv_m; A.adj_I = adj_I; A.adj_inv_I = adj_inv_I;
-    rollout_backward_kernel<<<grid_for(A.nwarps), PPR_BLOCK, 0, (cudaStream_t)stream>>>(m->d, A);
+    dim3 grid(grid_for(A.nwarps));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->variant == 0) rollout_backward_kernel<JM_REVOLUTE, false, false><<<grid, PPR_BLOCK, 0, st>>>(m->d, A);
+    else if (m->variant == 1) rollout_backward_kernel<JM_COMPOUND, false, false><<<grid, PPR_BLOCK, 0, st>>>(m->d, A);
+    else rollout_backward_kernel<JM_ALL, true, true><<<grid, PPR_BLOCK, 0, st>>>(m->d, A);
     g_launches++;
     return (int)cudaGetLastError();
 }
