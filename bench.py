@@ -172,7 +172,7 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     from ppr_diffphys_b200 import ForwardWarp, SimEnv, _lib, load_robot
-    from ppr_diffphys_b200.synth import make_batch, mass_chain
+    from ppr_diffphys_b200.synth import make_batch, mass_chain, shared_param_chain
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -202,10 +202,7 @@ def run_gpu_arm(args):
         q_init = inp["q_init"].detach().requires_grad_(True)
         qd_init = inp["qd_init"].detach().requires_grad_(True)
         refs = inp["refs"].detach().requires_grad_(True)
-        ke = p_ke[None].expand(bs, nqd).reshape(-1)
-        kd = p_kd[None].expand(bs, nqd).reshape(-1)
-        mass = p_mass[None].expand(bs, nb).reshape(-1)
-        inv_m, I, inv_I = mass_chain(mass, nI)
+        ke, kd, mass, inv_m, I, inv_I = shared_param_chain(p_ke, p_kd, p_mass, nI, bs)
         pos, vel = ForwardWarp.apply(q_init, qd_init, None, None, refs, ke, kd, mass, inv_m, I, inv_I, caller)
         loss = (pos[-1, :, :3] - pos[0, :, :3]).pow(2).mean() + 1e-3 * vel[-1].pow(2).mean()
         for p in (p_ke, p_kd, p_mass):

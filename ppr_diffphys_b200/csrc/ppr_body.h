@@ -183,6 +183,56 @@ template <class T> PPR_HD void revolute_angle_adj(V3<T> axis, Q4<T> r_err, T g_q
     g_rerr.x += g_d * axis.x; g_rerr.y += g_d * axis.y; g_rerr.z += g_d * axis.z;
 }
 
+// COMPOUND joint: XYZ-Euler decomposition of the relative rotation q_pc and the reconstructed rotation axes
+// (quat_decompose + axis reconstruction, integrator_euler.py:246-258,419-427):
+//   (a0,a1,a2) = -(atan2(c2.y,c2.z), asin(-c2.x), atan2(c1.x,c0.x)),  c_i = quat_rotate(q_pc, e_i)
+//   e0 = x,  e1 = R(q0) y,  e2 = R(q1 q0) z   with q0 = (x, a0), q1 = (e1, a1).
+// The reference rebuilds e1, e2 through sin/cos of the angles it just extracted with atan2/asin; the same functions
+// in closed form are  e1 = (0, cos a0, sin a0),  e2 = (sin a1, -sin a0 cos a1, cos a0 cos a1)  with
+//   cos a0 = c2.z/rho, sin a0 = -c2.y/rho, rho = |(c2.y,c2.z)|,  sin a1 = clamp(c2.x), cos a1 = sqrt(1 - sin^2 a1)
+// (q0, q1 are exactly unit, so R(q1 q0) = R(q1) R(q0)) -- no trigonometry besides the three inverse functions
+// that the PD law itself needs.
+template <class T> struct CompoundDec {
+    T c0x, c1x; V3<T> c2;
+    T ang[3];
+    T sa0, ca0, sa1, ca1;
+    V3<T> e1, e2;
+};
+template <class T> PPR_HD CompoundDec<T> compound_decompose(Q4<T> q_pc) {
+    CompoundDec<T> d;
+    V3<T> c0 = qrot(q_pc, v3<T>(T(1), T(0), T(0)));
+    V3<T> c1 = qrot(q_pc, v3<T>(T(0), T(1), T(0)));
+    d.c2 = qrot(q_pc, v3<T>(T(0), T(0), T(1)));
+    d.c0x = c0.x; d.c1x = c1.x;
+    d.ang[0] = -atan2(d.c2.y, d.c2.z);
+    d.ang[1] = -safe_asin(-d.c2.x);
+    d.ang[2] = -atan2(d.c1x, d.c0x);
+    T rho = sqrt(d.c2.y * d.c2.y + d.c2.z * d.c2.z);
+    if (rho > T(0)) { T ir = T(1) / rho; d.ca0 = d.c2.z * ir; d.sa0 = -d.c2.y * ir; }
+    else { d.ca0 = T(1); d.sa0 = T(0); }  // atan2(0,0) = 0
+    d.sa1 = clampT(d.c2.x, T(-1), T(1));
+    d.ca1 = sqrt(T(1) - d.sa1 * d.sa1);
+    d.e1 = v3<T>(T(0), d.ca0, d.sa0);
+    d.e2 = v3<T>(d.sa1, -d.sa0 * d.ca1, d.ca0 * d.ca1);
+    return d;
+}
+// adjoint: g_e1, g_e2 = adjoints of the axes, g_ang = adjoints of the angles (in/out: axis terms are added);
+// returns the adjoint of q_pc
+template <class T> PPR_HD Q4<T> compound_decompose_adj(Q4<T> q_pc, const CompoundDec<T>& d, V3<T> g_e1, V3<T> g_e2,
+                                                       T* g_ang) {
+    g_ang[0] += -d.sa0 * g_e1.y + d.ca0 * g_e1.z - d.ca0 * d.ca1 * g_e2.y - d.sa0 * d.ca1 * g_e2.z;
+    g_ang[1] += d.ca1 * g_e2.x + d.sa0 * d.sa1 * g_e2.y - d.ca0 * d.sa1 * g_e2.z;
+    T g_phi = -g_ang[0], g_theta = -g_ang[1], g_psi = -g_ang[2];
+    V3<T> g_c0 = vzero<T>(), g_c1 = vzero<T>(), g_c2 = vzero<T>();
+    T den = d.c2.y * d.c2.y + d.c2.z * d.c2.z;
+    if (den > T(0)) { T id = T(1) / den; g_c2.y += g_phi * d.c2.z * id; g_c2.z -= g_phi * d.c2.y * id; }
+    g_c2.x += -g_theta * safe_asin_adj(-d.c2.x);
+    den = d.c1x * d.c1x + d.c0x * d.c0x;
+    if (den > T(0)) { T id = T(1) / den; g_c1.x += g_psi * d.c0x * id; g_c0.x -= g_psi * d.c1x * id; }
+    return qrot_adj_q(q_pc, v3<T>(T(1), T(0), T(0)), g_c0) + qrot_adj_q(q_pc, v3<T>(T(0), T(1), T(0)), g_c1) +
+           qrot_adj_q(q_pc, v3<T>(T(0), T(0), T(1)), g_c2);
+}
+
 // Forward joint wrench. P = parent body (identity / zero twist if the joint has no parent), xcp / xcc = world COMs.
 // Outputs the joint torque t and force f together with the two moment arms; the caller applies
 //   F_parent += (t + arm_p x f, f),  F_child -= (t + arm_c x f, f)      (integrator_euler.py:448-451)
@@ -210,17 +260,10 @@ PPR_HD void joint_fwd(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
         f_out = x_err * ake + v_err * akd;
     } else if (JM != JM_REVOLUTE && js.type == JT_COMPOUND) {
         Q4<T> q_pc = QOFF ? qmul(qmul(qconj(js.qoff), r_err), js.qoff) : r_err;
-        V3<T> c0 = qrot(q_pc, v3<T>(T(1), T(0), T(0)));
-        V3<T> c1 = qrot(q_pc, v3<T>(T(0), T(1), T(0)));
-        V3<T> c2 = qrot(q_pc, v3<T>(T(0), T(0), T(1)));
-        T ang[3] = {-atan2(c2.y, c2.z), -safe_asin(-c2.x), -atan2(c1.x, c0.x)};
-        V3<T> a0 = v3<T>(T(1), T(0), T(0));
-        Q4<T> q0 = q_axis_angle(a0, ang[0]);
-        V3<T> a1 = qrot(q0, v3<T>(T(0), T(1), T(0)));
-        Q4<T> q1 = q_axis_angle(a1, ang[1]);
-        V3<T> a2 = qrot(qmul(q1, q0), v3<T>(T(0), T(0), T(1)));
+        CompoundDec<T> dec = compound_decompose(q_pc);
+        const T* ang = dec.ang;
         Q4<T> qw = QOFF ? qmul(qA, js.qoff) : qA;
-        V3<T> ax[3] = {a0, a1, a2};
+        V3<T> ax[3] = {v3<T>(T(1), T(0), T(0)), dec.e1, dec.e2};
         V3<T> t = vzero<T>();
 PPR_UNROLL
         for (int k = 0; k < 3; ++k) {
@@ -313,16 +356,11 @@ PPR_HD void joint_adj(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
     }
     if (JM != JM_REVOLUTE && js.type == JT_COMPOUND) {
         Q4<T> q_pc = QOFF ? qmul(qmul(qconj(js.qoff), r_err), js.qoff) : r_err;
-        const V3<T> ex = v3<T>(T(1), T(0), T(0)), ey = v3<T>(T(0), T(1), T(0)), ez = v3<T>(T(0), T(0), T(1));
-        V3<T> c0 = qrot(q_pc, ex), c1 = qrot(q_pc, ey), c2v = qrot(q_pc, ez);
-        T ang[3] = {-atan2(c2v.y, c2v.z), -safe_asin(-c2v.x), -atan2(c1.x, c0.x)};
-        Q4<T> q0 = q_axis_angle(ex, ang[0]);
-        V3<T> a1 = qrot(q0, ey);
-        Q4<T> q1 = q_axis_angle(a1, ang[1]);
-        Q4<T> q10 = qmul(q1, q0);
-        V3<T> a2 = qrot(q10, ez);
+        const V3<T> ex = v3<T>(T(1), T(0), T(0));
+        CompoundDec<T> dec = compound_decompose(q_pc);
+        const T* ang = dec.ang;
         Q4<T> qw = QOFF ? qmul(qA, js.qoff) : qA;
-        V3<T> ax[3] = {ex, a1, a2};
+        V3<T> ax[3] = {ex, dec.e1, dec.e2};
         V3<T> aw[3];
         T qd[3], sc[3];
         V3<T> traw = vzero<T>();
@@ -356,23 +394,7 @@ PPR_UNROLL
             g_qw += qrot_adj_q(qw, ax[k], g_aw);
             g_ax[k] += qrot_inv(qw, g_aw);
         }
-        // a2 = qrot(q10, ez); q10 = q1*q0
-        Q4<T> g_q10 = qrot_adj_q(q10, ez, g_ax[2]);
-        Q4<T> g_q1 = qmul(g_q10, qconj(q0));
-        Q4<T> g_q0 = qmul(qconj(q1), g_q10);
-        g_ang[1] += q_axis_angle_adj(a1, ang[1], g_q1, g_ax[1]);
-        g_q0 += qrot_adj_q(q0, ey, g_ax[1]);
-        V3<T> dummy = vzero<T>();
-        g_ang[0] += q_axis_angle_adj(ex, ang[0], g_q0, dummy);
-        // ang = -(phi, theta, psi)
-        T g_phi = -g_ang[0], g_theta = -g_ang[1], g_psi = -g_ang[2];
-        V3<T> g_c0 = vzero<T>(), g_c1 = vzero<T>(), g_c2 = vzero<T>();
-        T den = c2v.y * c2v.y + c2v.z * c2v.z;
-        if (den > T(0)) { g_c2.y += g_phi * c2v.z / den; g_c2.z -= g_phi * c2v.y / den; }
-        g_c2.x += -g_theta * safe_asin_adj(-c2v.x);
-        den = c1.x * c1.x + c0.x * c0.x;
-        if (den > T(0)) { g_c1.x += g_psi * c0.x / den; g_c0.x -= g_psi * c1.x / den; }
-        Q4<T> g_qpc = qrot_adj_q(q_pc, ex, g_c0) + qrot_adj_q(q_pc, ey, g_c1) + qrot_adj_q(q_pc, ez, g_c2);
+        Q4<T> g_qpc = compound_decompose_adj(q_pc, dec, g_ax[1], g_ax[2], g_ang);
         // q_pc = (conj(qoff) * r_err) * qoff ; qw = qA * qoff
         if (QOFF) {
             g_rerr += qmul(js.qoff, qmul(g_qpc, qconj(js.qoff)));

@@ -28,7 +28,8 @@ typedef Body<float> BodyF;
 typedef Wrench<float> WrenchF;
 
 #define PPR_MAX_CHILD 8
-#define PPR_CKPT_FLOATS 19  // body_q 7 + body_qd 6 + total wrench 6
+#define PPR_CKPT_FLOATS 24  // body_q 7 + body_qd 6 + total wrench 6 + active-contact record 5 (count, 8 x u16)
+#define PPR_REC_MAX 8
 #define PPR_BLOCK 128
 #define PPR_WARPS (PPR_BLOCK / 32)
 #define PPR_CLIST_CAP 16  // penetrating points listed per body before falling back to the cooperative path
@@ -146,9 +147,9 @@ __device__ __forceinline__ ContactMat<float> mat_of(const DevModel& M, const Con
 //     PPR_CLIST_CAP penetrate (owner falls back to the cooperative evaluate-and-reduce path).
 // The test uses a 1e-6 m margin; the exact `c > 0` rejection of the reference is re-applied per point in phase B.
 __device__ __forceinline__ int contact_candidates(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
-                                                  int* __restrict__ clist) {
+                                                  int* __restrict__ clist, float& m0, float& m1, float& m2) {
     float w = s.r.w, ux = s.r.x, uy = s.r.y, uz = s.r.z;
-    float m0 = 2.f * (w * uz + uy * ux), m1 = 2.f * w * w - 1.f + 2.f * uy * uy, m2 = 2.f * (uy * uz - w * ux);
+    m0 = 2.f * (w * uz + uy * ux); m1 = 2.f * w * w - 1.f + 2.f * uy * uy; m2 = 2.f * (uy * uz - w * ux);
     float ylow = s.x.y + fminf(m0 * L.aabb[0], m0 * L.aabb[3]) + fminf(m1 * L.aabb[1], m1 * L.aabb[4]) +
                  fminf(m2 * L.aabb[2], m2 * L.aabb[5]) - L.aabb[6];
     bool maybe = L.valid && (L.c1 > L.c0) && !(ylow > 1e-6f);
@@ -163,20 +164,25 @@ __device__ __forceinline__ int contact_candidates(const DevModel& M, const LaneI
         float a0 = shf(m0, a), a1 = shf(m1, a), a2 = shf(m2, a), ay = shf(s.x.y, a);
         int c0 = __shfl_sync(FULL, L.c0, a), c1 = __shfl_sync(FULL, L.c1, a);
         int cnt = 0;
-        for (int base = c0; base < c1; base += 32) {
-            int k = base + lane;
-            bool pen = false;
-            if (k < c1) {
-                float4 p = M.cpt[k];
-                float c = ay + a0 * p.x + a1 * p.y + a2 * p.z - p.w;
-                pen = !(c > 1e-6f);
+        for (int base = c0; base < c1; base += 128) {
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // all loads of the trip in flight before the first use
+                int k = base + u * 32 + lane;
+                p[u] = (k < c1) ? M.cpt[k] : make_float4(0.f, 0.f, 0.f, -1e30f);
             }
-            unsigned bits = __ballot_sync(FULL, pen);
-            if (pen) {
-                int pos = cnt + __popc(bits & lt);
-                if (pos < PPR_CLIST_CAP) clist[a * PPR_CLIST_STRIDE + pos] = k;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int k = base + u * 32 + lane;
+                float c = ay + a0 * p[u].x + a1 * p[u].y + a2 * p[u].z - p[u].w;
+                bool pen = !(c > 1e-6f);
+                unsigned bits = __ballot_sync(FULL, pen);
+                if (pen) {
+                    int pos = cnt + __popc(bits & lt);
+                    if (pos < PPR_CLIST_CAP) clist[a * PPR_CLIST_STRIDE + pos] = k;
+                }
+                cnt += __popc(bits);
             }
-            cnt += __popc(bits);
         }
         if (lane == a) mine = cnt > PPR_CLIST_CAP ? -1 : cnt;
     }
@@ -184,22 +190,43 @@ __device__ __forceinline__ int contact_candidates(const DevModel& M, const LaneI
     return mine;
 }
 
+// record of the contact points that actually produced force in a substep (consumed by the adjoint kernel)
+struct ContactRec {
+    unsigned cnt;              // number of active points; > PPR_REC_MAX = not recorded (adjoint re-derives them)
+    unsigned long long lo, hi; // 8 x u16 point indices
+};
+__device__ __forceinline__ void rec_push(ContactRec& r, int k) {
+    if (r.cnt < 4) r.lo |= (unsigned long long)(unsigned)k << (16 * r.cnt);
+    else if (r.cnt < 8) r.hi |= (unsigned long long)(unsigned)k << (16 * (r.cnt - 4));
+    r.cnt++;
+}
+__device__ __forceinline__ int rec_get(const ContactRec& r, unsigned i) {
+    unsigned long long w = i < 4 ? r.lo : r.hi;
+    return (int)((w >> (16 * (i & 3))) & 0xffffull);
+}
+
 // K3 for the whole warp: subtracts contact wrenches from F (per lane = per body)
 __device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
-                                                  const ContactMat<float>& cm0, int* __restrict__ clist, WrenchF& F) {
-    int cand = contact_candidates(M, L, lane, s, clist);
+                                                  const ContactMat<float>& cm0, int* __restrict__ clist, WrenchF& F,
+                                                  ContactRec& rec) {
+    float m0, m1, m2;
+    int cand = contact_candidates(M, L, lane, s, clist, m0, m1, m2);
+    rec.cnt = 0; rec.lo = 0ull; rec.hi = 0ull;
+    const bool can_rec = M.nc <= 65535;
     if (cand == -2) {
         for (int k = L.c0; k < L.c1; ++k) {
             float4 p = M.cpt[k];
-            contact_point_fwd(s, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), F);
+            if (s.x.y + m0 * p.x + m1 * p.y + m2 * p.z - p.w > 1e-6f) continue;  // cheap conservative reject
+            if (contact_point_fwd(s, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), F)) rec_push(rec, k);
         }
     } else {
         for (int i = 0; i < cand; ++i) {
             int k = clist[lane * PPR_CLIST_STRIDE + i];
             float4 p = M.cpt[k];
-            contact_point_fwd(s, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), F);
+            if (contact_point_fwd(s, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), F)) rec_push(rec, k);
         }
     }
+    if (cand == -1 || !can_rec) rec.cnt = PPR_REC_MAX + 1;
     unsigned mask = __ballot_sync(FULL, cand == -1);
     while (mask) {  // many penetrating points: evaluate cooperatively and reduce
         int a = __ffs(mask) - 1;
@@ -219,11 +246,23 @@ __device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneI
     __syncwarp();  // clist is reused by the next substep
 }
 
-// K3^T for the whole warp
+// K3^T for the whole warp. Normally only replays the points the forward pass recorded as active; lanes whose
+// record overflowed (> PPR_REC_MAX active points) re-derive them like the forward pass did.
 __device__ __forceinline__ void warp_contacts_adj(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
                                                   const ContactMat<float>& cm0, int* __restrict__ clist,
-                                                  const WrenchF& adjF, BodyF& adjS, F3& adj_xc) {
-    int cand = contact_candidates(M, L, lane, s, clist);
+                                                  const ContactRec& rec, const WrenchF& adjF, BodyF& adjS, F3& adj_xc) {
+    const bool ovf = L.valid && rec.cnt > PPR_REC_MAX;
+    if (!ovf && L.valid) {
+        for (unsigned i = 0; i < rec.cnt; ++i) {
+            int k = rec_get(rec, i);
+            float4 p = M.cpt[k];
+            contact_point_adj(s, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), adjF, adjS, adj_xc);
+        }
+    }
+    if (!__any_sync(FULL, ovf)) return;
+    float m0, m1, m2;
+    int cand = contact_candidates(M, L, lane, s, clist, m0, m1, m2);
+    if (!ovf) cand = 0;
     if (cand == -2) {
         for (int k = L.c0; k < L.c1; ++k) {
             float4 p = M.cpt[k];
@@ -274,13 +313,11 @@ __device__ __forceinline__ BodyF warp_fk(const DevModel& M, const LaneInfo& L, c
 
 // sum over this lane's children of a Body-shaped quantity held by the child lanes
 __device__ __forceinline__ void gather_children_body(const DevModel& M, const LaneInfo& L, const BodyF& mine, BodyF& acc) {
-#pragma unroll
-    for (int sl = 0; sl < PPR_MAX_CHILD; ++sl) {
-        if (sl < M.maxc) {
-            unsigned c = (unsigned)((L.child >> (8 * sl)) & 0xffu);
-            BodyF o = shf_body(mine, c == 0xffu ? 0 : (int)c);
-            if (c != 0xffu) body_acc(acc, o);
-        }
+#pragma unroll 1
+    for (int sl = 0; sl < M.maxc; ++sl) {
+        unsigned c = (unsigned)((L.child >> (8 * sl)) & 0xffu);
+        BodyF o = shf_body(mine, c == 0xffu ? 0 : (int)c);
+        if (c != 0xffu) body_acc(acc, o);
     }
 }
 
@@ -391,13 +428,14 @@ __device__ __forceinline__ void store_wrench_row(float* base, const WrenchF& w) 
 template <int JM, bool LIMITS, bool QOFF>
 __device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
                                             const JointCtl<float>& ctl, const ContactMat<float>& cm0, int* clist,
-                                            const float* res_f_row, float* grf_row, float* jaf_row, WrenchF& F) {
+                                            const float* res_f_row, float* grf_row, float* jaf_row, WrenchF& F,
+                                            ContactRec& rec) {
     F = wrench_zero<float>();
     if (res_f_row && L.valid) {
         F.t = v3<float>(res_f_row[0], res_f_row[1], res_f_row[2]);
         F.f = v3<float>(res_f_row[3], res_f_row[4], res_f_row[5]);
     }
-    warp_contacts_fwd(M, L, lane, s, xc, cm0, clist, F);
+    warp_contacts_fwd(M, L, lane, s, xc, cm0, clist, F, rec);
     WrenchF G = F;
     if (grf_row && L.valid) store_wrench_row(grf_row, F);
     // joints: this lane is the child of its joint
@@ -411,13 +449,11 @@ __device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L
         F.t -= t + cross(ac, f); F.f -= f;
         if (L.has_parent) { Wp.t = t + cross(ap, f); Wp.f = f; }
     }
-#pragma unroll
-    for (int sl = 0; sl < PPR_MAX_CHILD; ++sl) {
-        if (sl < M.maxc) {
-            unsigned c = (unsigned)((L.child >> (8 * sl)) & 0xffu);
-            WrenchF o = shf_wrench(Wp, c == 0xffu ? 0 : (int)c);
-            if (c != 0xffu) { F.t += o.t; F.f += o.f; }
-        }
+#pragma unroll 1
+    for (int sl = 0; sl < M.maxc; ++sl) {
+        unsigned c = (unsigned)((L.child >> (8 * sl)) & 0xffu);
+        WrenchF o = shf_wrench(Wp, c == 0xffu ? 0 : (int)c);
+        if (c != 0xffu) { F.t += o.t; F.f += o.f; }
     }
     if (jaf_row && L.valid) {
         WrenchF J; J.t = F.t - G.t; J.f = F.f - G.f;
@@ -481,9 +517,10 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         F3 xc = s.x + qrot(s.r, L.com);
         load_ctl(M, L, A, t, ke, kd, ctl);
         WrenchF F;
+        ContactRec rec;
         warp_forces<JM, LIMITS, QOFF>(M, L, lane, s, xc, ctl, cm0, clist, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
                     (frame && A.out_grf) ? A.out_grf + frow * 6 : nullptr,
-                    (frame && A.out_jaf) ? A.out_jaf + frow * 6 : nullptr, F);
+                    (frame && A.out_jaf) ? A.out_jaf + frow * 6 : nullptr, F, rec);
         // checkpoint (coalesced: component-major rows of 32 lanes)
         float* c = ck + t * ck_step;
         c[0 * 32] = s.x.x; c[1 * 32] = s.x.y; c[2 * 32] = s.x.z;
@@ -492,6 +529,9 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         c[10 * 32] = s.v.x; c[11 * 32] = s.v.y; c[12 * 32] = s.v.z;
         c[13 * 32] = F.t.x; c[14 * 32] = F.t.y; c[15 * 32] = F.t.z;
         c[16 * 32] = F.f.x; c[17 * 32] = F.f.y; c[18 * 32] = F.f.z;
+        c[19 * 32] = __uint_as_float(rec.cnt);
+        c[20 * 32] = __uint_as_float((unsigned)rec.lo); c[21 * 32] = __uint_as_float((unsigned)(rec.lo >> 32));
+        c[22 * 32] = __uint_as_float((unsigned)rec.hi); c[23 * 32] = __uint_as_float((unsigned)(rec.hi >> 32));
         s = integrate_fwd(s, xc, L.com, F, inv_m, I, inv_I, g, A.dt);
     }
 }
@@ -571,6 +611,10 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         s.v = v3<float>(c[10 * 32], c[11 * 32], c[12 * 32]);
         F.t = v3<float>(c[13 * 32], c[14 * 32], c[15 * 32]);
         F.f = v3<float>(c[16 * 32], c[17 * 32], c[18 * 32]);
+        ContactRec rec;
+        rec.cnt = __float_as_uint(c[19 * 32]);
+        rec.lo = (unsigned long long)__float_as_uint(c[20 * 32]) | ((unsigned long long)__float_as_uint(c[21 * 32]) << 32);
+        rec.hi = (unsigned long long)__float_as_uint(c[22 * 32]) | ((unsigned long long)__float_as_uint(c[23 * 32]) << 32);
         F3 xc = s.x + qrot(s.r, L.com);
         load_ctl(M, L, A, tp, ke, kd, ctl);
         // K5^T
@@ -605,7 +649,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
             }
         }
         // K3^T
-        warp_contacts_adj(M, L, lane, s, xc, cm0, clist, adjF, adjS, adj_xc);
+        warp_contacts_adj(M, L, lane, s, xc, cm0, clist, rec, adjF, adjS, adj_xc);
         // K2^T
         if (A.adj_res_f && L.valid) store_wrench_row(A.adj_res_f + ((tp * A.bs + L.env) * M.nb + L.body) * 6, adjF);
         // world COM -> pose

@@ -61,3 +61,15 @@ def mass_chain(body_mass, norm_body_inertia):
     I = nI[None].repeat(bs, 1, 1, 1).view(-1, 3, 3) * body_mass[..., None, None]
     inv_I = torch.linalg.inv(I).contiguous()
     return inv_m, I, inv_I
+
+
+def shared_param_chain(target_ke, target_kd, body_mass, norm_body_inertia, bs):
+    """Shared parameters [nqd], [nqd], [nb] -> the per-env replicated tensors ForwardWarp.apply expects
+    (dp_model.py:723-730).  Same values as the reference's chain, but the 3x3 inverse is taken on the nb shared
+    matrices BEFORE replication instead of on bs*nb copies of them; autograd sums the per-env gradients back."""
+    nb = body_mass.numel()
+    inv_m = 1.0 / body_mass
+    I = norm_body_inertia * body_mass[:, None, None]
+    inv_I = torch.linalg.inv(I)
+    rep = lambda t: t[None].expand(bs, *t.shape).reshape(bs * t.shape[0], *t.shape[1:])
+    return rep(target_ke), rep(target_kd), rep(body_mass), rep(inv_m), rep(I), rep(inv_I)
