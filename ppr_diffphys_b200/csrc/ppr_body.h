@@ -478,10 +478,13 @@ PPR_HD Body<T> integrate_fwd(const Body<T>& b, V3<T> xc, V3<T> com, const Wrench
     return o;
 }
 
+// Core of K5^T. The inertia-parameter adjoints are rank-1 updates; they are returned as their factors
+//   adj_I += gI_a (x) gI_b ,  adj_inv_I += giI_a (x) giI_b      (giI_a already carries the factor dt)
+// so that a caller can accumulate them wherever it likes (the CUDA adjoint keeps the accumulators in shared memory).
 template <class T>
-PPR_HD void integrate_adj(const Body<T>& b, V3<T> xc, V3<T> com, const Wrench<T>& F, T inv_m, const T* I,
-                          const T* inv_I, V3<T> g, T dt, const Body<T>& adjO, Body<T>& adjB, V3<T>& adj_xc,
-                          Wrench<T>& adjF, T& adj_inv_m, T* adj_I, T* adj_inv_I) {
+PPR_HD void integrate_adj_core(const Body<T>& b, V3<T> xc, V3<T> com, const Wrench<T>& F, T inv_m, const T* I,
+                               const T* inv_I, V3<T> g, T dt, const Body<T>& adjO, Body<T>& adjB, V3<T>& adj_xc,
+                               Wrench<T>& adjF, T& adj_inv_m, V3<T>& gI_a, V3<T>& gI_b, V3<T>& giI_a, V3<T>& giI_b) {
     // ---- recompute
     T nz = inv_m != T(0) ? T(1) : T(0);
     V3<T> v1 = b.v + (F.f * inv_m + g * nz) * dt;
@@ -509,14 +512,14 @@ PPR_HD void integrate_adj(const Body<T>& b, V3<T> xc, V3<T> com, const Wrench<T>
     V3<T> g_wb2 = qrot_inv(b.r, g_w1);
     V3<T> g_wb = g_wb2;
     V3<T> g_tb = matTvec(inv_I, g_wb2) * dt;
-    outer_acc(adj_inv_I, g_wb2, tb, dt);
+    giI_a = g_wb2 * dt; giI_b = tb;
     adjF.t = qrot(b.r, g_tb);
     adjB.r += qrotinv_adj_q(b.r, F.t, g_tb);
     V3<T> g_c = -g_tb;  // c = wb x Iwb
     g_wb += cross(Iwb, g_c);
     V3<T> g_Iwb = cross(g_c, wb);
     g_wb += matTvec(I, g_Iwb);
-    outer_acc(adj_I, g_Iwb, wb, T(1));
+    gI_a = g_Iwb; gI_b = wb;
     adjB.w += qrot(b.r, g_wb);
     adjB.r += qrotinv_adj_q(b.r, b.w, g_wb);
     adj_xc += g_x1c;
@@ -524,6 +527,16 @@ PPR_HD void integrate_adj(const Body<T>& b, V3<T> xc, V3<T> com, const Wrench<T>
     V3<T> g_a = g_v1 * dt;
     adjF.f = g_a * inv_m;
     adj_inv_m += dot(F.f, g_a);
+}
+
+template <class T>
+PPR_HD void integrate_adj(const Body<T>& b, V3<T> xc, V3<T> com, const Wrench<T>& F, T inv_m, const T* I,
+                          const T* inv_I, V3<T> g, T dt, const Body<T>& adjO, Body<T>& adjB, V3<T>& adj_xc,
+                          Wrench<T>& adjF, T& adj_inv_m, T* adj_I, T* adj_inv_I) {
+    V3<T> a, bb, c, d;
+    integrate_adj_core(b, xc, com, F, inv_m, I, inv_I, g, dt, adjO, adjB, adj_xc, adjF, adj_inv_m, a, bb, c, d);
+    outer_acc(adj_I, a, bb, T(1));
+    outer_acc(adj_inv_I, c, d, T(1));
 }
 
 // ------------------------------------------------------------------------------------------ FK (K1)

@@ -88,6 +88,17 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Shared-memory residency of everything that is constant over the time loop, so that it does not occupy
+// registers for the whole rollout (the kernels are occupancy/latency bound):
+//   static per-BODY table  sm_st[PPR_NSTATIC][32]   (indexed by body; lanes of different envs broadcast-read)
+//   per-LANE parameters    sm_par[PPR_NPAR][PPR_BLOCK]  inv_m, I[9], inv_I[9]
+//   per-LANE accumulators  sm_acc[18][PPR_BLOCK]        adj_I, adj_inv_I        (adjoint kernel only)
+// Reads go through volatile pointers so that ptxas re-issues the (29-cycle) LDS at the point of use instead of
+// hoisting the values back into loop-long registers.
+#define PPR_NSTATIC 28  // xpj 3, qpj 4, axis 3, com 3, parent com 3, aabb 7, qoff 4, pad 1
+#define PPR_NPAR 19
+enum { ST_XPJ = 0, ST_QPJ = 3, ST_AXIS = 7, ST_COM = 10, ST_CPAR = 13, ST_AABB = 16, ST_QOFF = 23 };
+
 struct LaneInfo {
     int env, body, parent_lane, type, ndof, depth, qs, qds, c0, c1;
     bool valid, has_parent;
@@ -129,6 +140,40 @@ __device__ __forceinline__ LaneInfo lane_setup(const DevModel& M, int64_t warp, 
     return L;
 }
 
+__device__ __forceinline__ void stage_static(volatile float* st, const LaneInfo& L, F3 com_par) {
+    int b = L.body;
+    st[(ST_XPJ + 0) * 32 + b] = L.js.xpj.x; st[(ST_XPJ + 1) * 32 + b] = L.js.xpj.y; st[(ST_XPJ + 2) * 32 + b] = L.js.xpj.z;
+    st[(ST_QPJ + 0) * 32 + b] = L.js.qpj.x; st[(ST_QPJ + 1) * 32 + b] = L.js.qpj.y;
+    st[(ST_QPJ + 2) * 32 + b] = L.js.qpj.z; st[(ST_QPJ + 3) * 32 + b] = L.js.qpj.w;
+    st[(ST_AXIS + 0) * 32 + b] = L.js.axis.x; st[(ST_AXIS + 1) * 32 + b] = L.js.axis.y; st[(ST_AXIS + 2) * 32 + b] = L.js.axis.z;
+    st[(ST_COM + 0) * 32 + b] = L.com.x; st[(ST_COM + 1) * 32 + b] = L.com.y; st[(ST_COM + 2) * 32 + b] = L.com.z;
+    st[(ST_CPAR + 0) * 32 + b] = com_par.x; st[(ST_CPAR + 1) * 32 + b] = com_par.y; st[(ST_CPAR + 2) * 32 + b] = com_par.z;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) st[(ST_AABB + i) * 32 + b] = L.aabb[i];
+    st[(ST_QOFF + 0) * 32 + b] = L.js.qoff.x; st[(ST_QOFF + 1) * 32 + b] = L.js.qoff.y;
+    st[(ST_QOFF + 2) * 32 + b] = L.js.qoff.z; st[(ST_QOFF + 3) * 32 + b] = L.js.qoff.w;
+}
+__device__ __forceinline__ F3 st_vec3(const volatile float* st, int row, int b) {
+    return v3<float>(st[row * 32 + b], st[(row + 1) * 32 + b], st[(row + 2) * 32 + b]);
+}
+template <bool QOFF>
+__device__ __forceinline__ JointStatic<float> st_joint(const volatile float* st, int b, int type) {
+    JointStatic<float> js;
+    js.type = type;
+    js.xpj = st_vec3(st, ST_XPJ, b);
+    js.qpj = q4<float>(st[(ST_QPJ + 0) * 32 + b], st[(ST_QPJ + 1) * 32 + b], st[(ST_QPJ + 2) * 32 + b],
+                       st[(ST_QPJ + 3) * 32 + b]);
+    js.axis = st_vec3(st, ST_AXIS, b);
+    js.qoff = QOFF ? q4<float>(st[(ST_QOFF + 0) * 32 + b], st[(ST_QOFF + 1) * 32 + b], st[(ST_QOFF + 2) * 32 + b],
+                               st[(ST_QOFF + 3) * 32 + b])
+                   : q4<float>(0.f, 0.f, 0.f, 1.f);
+    return js;
+}
+__device__ __forceinline__ void par_load9(const volatile float* par, int row0, float* out) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) out[i] = par[(row0 + i) * PPR_BLOCK];
+}
+
 __device__ __forceinline__ ContactMat<float> load_mat(const DevModel& M, int k) {
     float4 m = M.mats[M.cmat[k]];
     ContactMat<float> c; c.ke = m.x; c.kd = m.y; c.kf = m.z; c.mu = m.w;
@@ -147,11 +192,14 @@ __device__ __forceinline__ ContactMat<float> mat_of(const DevModel& M, const Con
 //     PPR_CLIST_CAP penetrate (owner falls back to the cooperative evaluate-and-reduce path).
 // The test uses a 1e-6 m margin; the exact `c > 0` rejection of the reference is re-applied per point in phase B.
 __device__ __forceinline__ int contact_candidates(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
-                                                  int* __restrict__ clist, float& m0, float& m1, float& m2) {
+                                                  const volatile float* st, int* __restrict__ clist, float& m0,
+                                                  float& m1, float& m2) {
     float w = s.r.w, ux = s.r.x, uy = s.r.y, uz = s.r.z;
     m0 = 2.f * (w * uz + uy * ux); m1 = 2.f * w * w - 1.f + 2.f * uy * uy; m2 = 2.f * (uy * uz - w * ux);
-    float ylow = s.x.y + fminf(m0 * L.aabb[0], m0 * L.aabb[3]) + fminf(m1 * L.aabb[1], m1 * L.aabb[4]) +
-                 fminf(m2 * L.aabb[2], m2 * L.aabb[5]) - L.aabb[6];
+    const int b = L.body;
+    float ylow = s.x.y + fminf(m0 * st[(ST_AABB + 0) * 32 + b], m0 * st[(ST_AABB + 3) * 32 + b]) +
+                 fminf(m1 * st[(ST_AABB + 1) * 32 + b], m1 * st[(ST_AABB + 4) * 32 + b]) +
+                 fminf(m2 * st[(ST_AABB + 2) * 32 + b], m2 * st[(ST_AABB + 5) * 32 + b]) - st[(ST_AABB + 6) * 32 + b];
     bool maybe = L.valid && (L.c1 > L.c0) && !(ylow > 1e-6f);
     bool big = (L.c1 - L.c0) > M.big_threshold;
     int mine = (maybe && !big) ? -2 : 0;
@@ -207,10 +255,10 @@ __device__ __forceinline__ int rec_get(const ContactRec& r, unsigned i) {
 
 // K3 for the whole warp: subtracts contact wrenches from F (per lane = per body)
 __device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
-                                                  const ContactMat<float>& cm0, int* __restrict__ clist, WrenchF& F,
-                                                  ContactRec& rec) {
+                                                  const ContactMat<float>& cm0, const volatile float* st,
+                                                  int* __restrict__ clist, WrenchF& F, ContactRec& rec) {
     float m0, m1, m2;
-    int cand = contact_candidates(M, L, lane, s, clist, m0, m1, m2);
+    int cand = contact_candidates(M, L, lane, s, st, clist, m0, m1, m2);
     rec.cnt = 0; rec.lo = 0ull; rec.hi = 0ull;
     const bool can_rec = M.nc <= 65535;
     if (cand == -2) {
@@ -249,8 +297,9 @@ __device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneI
 // K3^T for the whole warp. Normally only replays the points the forward pass recorded as active; lanes whose
 // record overflowed (> PPR_REC_MAX active points) re-derive them like the forward pass did.
 __device__ __forceinline__ void warp_contacts_adj(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
-                                                  const ContactMat<float>& cm0, int* __restrict__ clist,
-                                                  const ContactRec& rec, const WrenchF& adjF, BodyF& adjS, F3& adj_xc) {
+                                                  const ContactMat<float>& cm0, const volatile float* st,
+                                                  int* __restrict__ clist, const ContactRec& rec, const WrenchF& adjF,
+                                                  BodyF& adjS, F3& adj_xc) {
     const bool ovf = L.valid && rec.cnt > PPR_REC_MAX;
     if (!ovf && L.valid) {
         for (unsigned i = 0; i < rec.cnt; ++i) {
@@ -261,7 +310,7 @@ __device__ __forceinline__ void warp_contacts_adj(const DevModel& M, const LaneI
     }
     if (!__any_sync(FULL, ovf)) return;
     float m0, m1, m2;
-    int cand = contact_candidates(M, L, lane, s, clist, m0, m1, m2);
+    int cand = contact_candidates(M, L, lane, s, st, clist, m0, m1, m2);
     if (!ovf) cand = 0;
     if (cand == -2) {
         for (int k = L.c0; k < L.c1; ++k) {
@@ -427,15 +476,15 @@ __device__ __forceinline__ void store_wrench_row(float* base, const WrenchF& w) 
 // forces of one substep; F = total wrench on this lane's body. Optionally exports the grf / jaf side channels.
 template <int JM, bool LIMITS, bool QOFF>
 __device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
-                                            const JointCtl<float>& ctl, const ContactMat<float>& cm0, int* clist,
-                                            const float* res_f_row, float* grf_row, float* jaf_row, WrenchF& F,
-                                            ContactRec& rec) {
+                                            const JointCtl<float>& ctl, const ContactMat<float>& cm0,
+                                            const volatile float* st, int* clist, const float* res_f_row,
+                                            float* grf_row, float* jaf_row, WrenchF& F, ContactRec& rec) {
     F = wrench_zero<float>();
     if (res_f_row && L.valid) {
         F.t = v3<float>(res_f_row[0], res_f_row[1], res_f_row[2]);
         F.f = v3<float>(res_f_row[3], res_f_row[4], res_f_row[5]);
     }
-    warp_contacts_fwd(M, L, lane, s, xc, cm0, clist, F, rec);
+    warp_contacts_fwd(M, L, lane, s, xc, cm0, st, clist, F, rec);
     WrenchF G = F;
     if (grf_row && L.valid) store_wrench_row(grf_row, F);
     // joints: this lane is the child of its joint
@@ -443,7 +492,8 @@ __device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L
     F3 xcp = shf3(xc, L.parent_lane);
     if (!L.has_parent) { P = body_identity<float>(); xcp = vzero<float>(); }
     F3 t, f, ap, ac;
-    joint_fwd<float, JM, LIMITS, QOFF>(L.js, ctl, M.ake, M.akd, P, xcp, L.has_parent, s, xc, t, f, ap, ac);
+    joint_fwd<float, JM, LIMITS, QOFF>(st_joint<QOFF>(st, L.body, L.type), ctl, M.ake, M.akd, P, xcp, L.has_parent, s,
+                                       xc, t, f, ap, ac);
     WrenchF Wp = wrench_zero<float>();
     if (L.type != JT_FREE) {
         F.t -= t + cross(ac, f); F.f -= f;
@@ -461,29 +511,34 @@ __device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L
     }
 }
 
+// Resident blocks per SM asked of ptxas: 4 x 128 threads forward (<= 128 registers), 3 adjoint (<= 168). Measured
+// on B200 (profiles/README.md): issue-slot utilisation rises with resident warps; going further costs spills.
 #ifndef PPR_FWD_MINB
-#define PPR_FWD_MINB 1
+#define PPR_FWD_MINB 4
 #endif
 #ifndef PPR_BWD_MINB
-#define PPR_BWD_MINB 1
+#define PPR_BWD_MINB 3
 #endif
 template <int JM, bool LIMITS, bool QOFF>
 __global__ void __launch_bounds__(PPR_BLOCK, PPR_FWD_MINB)
 rollout_forward_kernel(DevModel M, RolloutArgs A) {
     __shared__ int clist_all[PPR_WARPS * 32 * PPR_CLIST_STRIDE];
+    __shared__ float sm_st[PPR_WARPS * PPR_NSTATIC * 32];
+    __shared__ float sm_par[PPR_NPAR * PPR_BLOCK];
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     int* clist = clist_all + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
+    volatile float* st = sm_st + (threadIdx.x >> 5) * PPR_NSTATIC * 32;
+    volatile float* par = sm_par + threadIdx.x;
     if (warp >= A.nwarps) return;
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
     if (M.nc > 0) cm0 = load_mat(M, 0);
     LaneInfo L = lane_setup(M, warp, lane, A.bs);
-    // per-env parameters of this body / joint
+    // per-env parameters of this body / joint -> shared memory
     int64_t eb = (int64_t)L.env * M.nb + L.body;
-    float inv_m = A.inv_m[eb];
-    float I[9], inv_I[9];
+    par[0] = A.inv_m[eb];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { I[i] = A.I[eb * 9 + i]; inv_I[i] = A.inv_I[eb * 9 + i]; }
+    for (int i = 0; i < 9; ++i) { par[(1 + i) * PPR_BLOCK] = A.I[eb * 9 + i]; par[(10 + i) * PPR_BLOCK] = A.inv_I[eb * 9 + i]; }
     JointCtl<float> ctl;
     float ke[3], kd[3];
 #pragma unroll
@@ -495,9 +550,14 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         ctl.lo[k] = lm.x; ctl.hi[k] = lm.y; ctl.lke[k] = lm.z; ctl.lkd[k] = lm.w;
     }
     F3 g = v3<float>(M.g[0], M.g[1], M.g[2]);
-    float jq[7], jqd[6];
-    load_joint_coords(L, A.q_init, A.qd_init, M.nq, M.nqd, jq, jqd);
-    BodyF s = warp_fk<JM>(M, L, jq, jqd);
+    BodyF s;
+    {
+        float jq[7], jqd[6];
+        load_joint_coords(L, A.q_init, A.qd_init, M.nq, M.nqd, jq, jqd);
+        s = warp_fk<JM>(M, L, jq, jqd);
+        stage_static(st, L, shf3(L.com, L.parent_lane));
+    }
+    __syncwarp();
 
     float* ck = A.ckpt + (warp * PPR_CKPT_FLOATS) * 32 + lane;
     const int64_t ck_step = A.nwarps * PPR_CKPT_FLOATS * 32;
@@ -514,11 +574,12 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         // the substep past the last frame exists only for the force side channels (dp_model.py:397): skip it
         // when nobody asked for them
         if (t == A.nsteps - 1 && !A.out_grf && !A.out_jaf) break;
-        F3 xc = s.x + qrot(s.r, L.com);
+        const F3 com = st_vec3(st, ST_COM, L.body);
+        F3 xc = s.x + qrot(s.r, com);
         load_ctl(M, L, A, t, ke, kd, ctl);
         WrenchF F;
         ContactRec rec;
-        warp_forces<JM, LIMITS, QOFF>(M, L, lane, s, xc, ctl, cm0, clist, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
+        warp_forces<JM, LIMITS, QOFF>(M, L, lane, s, xc, ctl, cm0, st, clist, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
                     (frame && A.out_grf) ? A.out_grf + frow * 6 : nullptr,
                     (frame && A.out_jaf) ? A.out_jaf + frow * 6 : nullptr, F, rec);
         // checkpoint (coalesced: component-major rows of 32 lanes)
@@ -532,7 +593,12 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         c[19 * 32] = __uint_as_float(rec.cnt);
         c[20 * 32] = __uint_as_float((unsigned)rec.lo); c[21 * 32] = __uint_as_float((unsigned)(rec.lo >> 32));
         c[22 * 32] = __uint_as_float((unsigned)rec.hi); c[23 * 32] = __uint_as_float((unsigned)(rec.hi >> 32));
-        s = integrate_fwd(s, xc, L.com, F, inv_m, I, inv_I, g, A.dt);
+        {
+            float I[9], inv_I[9];
+            par_load9(par, 1, I);
+            par_load9(par, 10, inv_I);
+            s = integrate_fwd(s, xc, com, F, par[0], I, inv_I, g, A.dt);
+        }
     }
 }
 
@@ -540,18 +606,25 @@ template <int JM, bool LIMITS, bool QOFF>
 __global__ void __launch_bounds__(PPR_BLOCK, PPR_BWD_MINB)
 rollout_backward_kernel(DevModel M, RolloutArgs A) {
     __shared__ int clist_all[PPR_WARPS * 32 * PPR_CLIST_STRIDE];
+    __shared__ float sm_st[PPR_WARPS * PPR_NSTATIC * 32];
+    __shared__ float sm_par[PPR_NPAR * PPR_BLOCK];
+    __shared__ float sm_acc[18 * PPR_BLOCK];
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     int* clist = clist_all + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
+    volatile float* st = sm_st + (threadIdx.x >> 5) * PPR_NSTATIC * 32;
+    volatile float* par = sm_par + threadIdx.x;
+    volatile float* acc = sm_acc + threadIdx.x;
     if (warp >= A.nwarps) return;
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
     if (M.nc > 0) cm0 = load_mat(M, 0);
     LaneInfo L = lane_setup(M, warp, lane, A.bs);
     int64_t eb = (int64_t)L.env * M.nb + L.body;
-    float inv_m = A.inv_m[eb];
-    float I[9], inv_I[9];
+    par[0] = A.inv_m[eb];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { I[i] = A.I[eb * 9 + i]; inv_I[i] = A.inv_I[eb * 9 + i]; }
+    for (int i = 0; i < 9; ++i) { par[(1 + i) * PPR_BLOCK] = A.I[eb * 9 + i]; par[(10 + i) * PPR_BLOCK] = A.inv_I[eb * 9 + i]; }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) acc[i * PPR_BLOCK] = 0.f;
     JointCtl<float> ctl;
     float ke[3], kd[3];
     const bool jon = L.type != JT_FREE;
@@ -565,11 +638,10 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     }
     F3 g = v3<float>(M.g[0], M.g[1], M.g[2]);
     // com of the parent body (to fold the parent's world-COM adjoint into its pose adjoint in the child lane)
-    F3 com_par = shf3(L.com, L.parent_lane);
+    stage_static(st, L, shf3(L.com, L.parent_lane));
+    __syncwarp();
 
-    float a_inv_m = 0.f, a_I[9], a_invI[9], a_ke[3] = {0, 0, 0}, a_kd[3] = {0, 0, 0};
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { a_I[i] = 0.f; a_invI[i] = 0.f; }
+    float a_inv_m = 0.f, a_ke[3] = {0, 0, 0}, a_kd[3] = {0, 0, 0};
 
     const float* ck = A.ckpt + (warp * PPR_CKPT_FLOATS) * 32 + lane;
     const int64_t ck_step = A.nwarps * PPR_CKPT_FLOATS * 32;
@@ -615,13 +687,30 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         rec.cnt = __float_as_uint(c[19 * 32]);
         rec.lo = (unsigned long long)__float_as_uint(c[20 * 32]) | ((unsigned long long)__float_as_uint(c[21 * 32]) << 32);
         rec.hi = (unsigned long long)__float_as_uint(c[22 * 32]) | ((unsigned long long)__float_as_uint(c[23 * 32]) << 32);
-        F3 xc = s.x + qrot(s.r, L.com);
+        const F3 com = st_vec3(st, ST_COM, L.body);
+        F3 xc = s.x + qrot(s.r, com);
         load_ctl(M, L, A, tp, ke, kd, ctl);
         // K5^T
         BodyF adjS = body_zero<float>();
         F3 adj_xc = vzero<float>();
         WrenchF adjF;
-        integrate_adj(s, xc, L.com, F, inv_m, I, inv_I, g, A.dt, adjN, adjS, adj_xc, adjF, a_inv_m, a_I, a_invI);
+        {
+            float I[9], inv_I[9];
+            par_load9(par, 1, I);
+            par_load9(par, 10, inv_I);
+            F3 ga, gb, gc, gd;
+            integrate_adj_core(s, xc, com, F, par[0], I, inv_I, g, A.dt, adjN, adjS, adj_xc, adjF, a_inv_m, ga, gb, gc,
+                               gd);
+            const float av[3] = {ga.x, ga.y, ga.z}, bv[3] = {gb.x, gb.y, gb.z};
+            const float cv[3] = {gc.x, gc.y, gc.z}, dv[3] = {gd.x, gd.y, gd.z};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    acc[(3 * i + j) * PPR_BLOCK] += av[i] * bv[j];
+                    acc[(9 + 3 * i + j) * PPR_BLOCK] += cv[i] * dv[j];
+                }
+        }
         // K4^T (this lane = child of its joint)
         BodyF P = shf_body(s, L.parent_lane);
         F3 xcp = shf3(xc, L.parent_lane);
@@ -630,10 +719,10 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         BodyF adjP = body_zero<float>();
         F3 adj_xcp = vzero<float>();
         float g_target[3] = {0, 0, 0}, g_act[3] = {0, 0, 0};
-        joint_adj<float, JM, LIMITS, QOFF>(L.js, ctl, M.ake, M.akd, P, xcp, L.has_parent, s, xc, adjFp, adjF, adjP,
-                                           adj_xcp, adjS, adj_xc, g_target, g_act, a_ke, a_kd);
+        joint_adj<float, JM, LIMITS, QOFF>(st_joint<QOFF>(st, L.body, L.type), ctl, M.ake, M.akd, P, xcp, L.has_parent, s,
+                                           xc, adjFp, adjF, adjP, adj_xcp, adjS, adj_xc, g_target, g_act, a_ke, a_kd);
         adjP.x += adj_xcp;
-        adjP.r += qrot_adj_q(P.r, com_par, adj_xcp);
+        adjP.r += qrot_adj_q(P.r, st_vec3(st, ST_CPAR, L.body), adj_xcp);
         if (!L.has_parent) adjP = body_zero<float>();
         gather_children_body(M, L, adjP, adjS);
         if (L.valid) {
@@ -649,25 +738,26 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
             }
         }
         // K3^T
-        warp_contacts_adj(M, L, lane, s, xc, cm0, clist, rec, adjF, adjS, adj_xc);
+        warp_contacts_adj(M, L, lane, s, xc, cm0, st, clist, rec, adjF, adjS, adj_xc);
         // K2^T
         if (A.adj_res_f && L.valid) store_wrench_row(A.adj_res_f + ((tp * A.bs + L.env) * M.nb + L.body) * 6, adjF);
         // world COM -> pose
         adjS.x += adj_xc;
-        adjS.r += qrot_adj_q(s.r, L.com, adj_xc);
+        adjS.r += qrot_adj_q(s.r, com, adj_xc);
         adjN = adjS;
     }
     // K1^T: state 0 = eval_fk(q_init, qd_init), recomputed
     {
         float jq[7], jqd[6];
-        load_joint_coords(L, A.q_init, A.qd_init, M.nq, M.nqd, jq, jqd);
-        BodyF s0 = warp_fk<JM>(M, L, jq, jqd);
-        warp_fk_adjoint<JM>(M, L, s0, adjN, jq, jqd, A.adj_q_init, A.adj_qd_init);
+        LaneInfo L2 = lane_setup(M, warp, lane, A.bs);  // re-derived: the static joint data lived in smem meanwhile
+        load_joint_coords(L2, A.q_init, A.qd_init, M.nq, M.nqd, jq, jqd);
+        BodyF s0 = warp_fk<JM>(M, L2, jq, jqd);
+        warp_fk_adjoint<JM>(M, L2, s0, adjN, jq, jqd, A.adj_q_init, A.adj_qd_init);
     }
     if (L.valid) {
         A.adj_inv_m[eb] = a_inv_m;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) { A.adj_I[eb * 9 + i] = a_I[i]; A.adj_inv_I[eb * 9 + i] = a_invI[i]; }
+        for (int i = 0; i < 9; ++i) { A.adj_I[eb * 9 + i] = acc[i * PPR_BLOCK]; A.adj_inv_I[eb * 9 + i] = acc[(9 + i) * PPR_BLOCK]; }
         int64_t d = (int64_t)L.env * M.nqd + L.qds;
 #pragma unroll
         for (int k = 0; k < 3; ++k) if (jon && k < L.ndof) { A.adj_ke[d + k] = a_ke[k]; A.adj_kd[d + k] = a_kd[k]; }
