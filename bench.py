@@ -202,7 +202,12 @@ def run_gpu_arm(args):
         q_init = inp["q_init"].detach().requires_grad_(True)
         qd_init = inp["qd_init"].detach().requires_grad_(True)
         refs = inp["refs"].detach().requires_grad_(True)
-        ke, kd, mass, inv_m, I, inv_I = shared_param_chain(p_ke, p_kd, p_mass, nI, bs)
+        if args.replicate_params:   # the reference's literal calling convention: per-env replicated parameters
+            ke, kd, mass, inv_m, I, inv_I = shared_param_chain(p_ke, p_kd, p_mass, nI, bs)
+        else:                       # un-replicated parameters: the kernels read one shared copy
+            ke, kd, mass = p_ke, p_kd, p_mass
+            inv_m, I = 1.0 / p_mass, nI * p_mass[:, None, None]
+            inv_I = torch.linalg.inv(I)
         pos, vel = ForwardWarp.apply(q_init, qd_init, None, None, refs, ke, kd, mass, inv_m, I, inv_I, caller)
         loss = (pos[-1, :, :3] - pos[0, :, :3]).pow(2).mean() + 1e-3 * vel[-1].pow(2).mean()
         for p in (p_ke, p_kd, p_mass):
@@ -214,7 +219,7 @@ def run_gpu_arm(args):
         if world > 1:
             dist.all_reduce(packed)
         if need_loss_host:
-            return float(loss), packed.cpu()
+            return float(loss.detach()), packed.cpu()
         return loss, packed
 
     dev_inp = {k: v.to(dev) for k, v in host.items()}
@@ -271,12 +276,38 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     fwd_ms = sum(e[0].elapsed_time(e[1]) for e in evs[1:]) / args.steps
     bwd_ms = sum(e[1].elapsed_time(e[2]) for e in evs[1:]) / args.steps
-    # ---- end-to-end: host (pinned) inputs -> device, step, loss + packed shared-parameter grads -> host
-    def e2e_step():
-        inp = {k: host[k].to(dev, non_blocking=True) for k in ("q_init", "qd_init", "refs")}
-        return step(inp, True)
-    e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    # ---- end-to-end: host (pinned) inputs -> device, step, loss + packed shared-parameter grads -> host.
+    # Every step's inputs are copied inside the timed region; the copy of step i+1 is issued on a copy stream
+    # (double-buffered device inputs) so that it overlaps the kernels of step i.
+    keys = ("q_init", "qd_init", "refs")
+    copy_stream = torch.cuda.Stream()
+    bufs = [{k: torch.empty_like(dev_inp[k]) for k in keys} for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+
+    def enqueue_copy(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[i % 2])
+            for k in keys:
+                bufs[i % 2][k].copy_(host[k], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def e2e_run(steps):
+        cur = torch.cuda.current_stream()
+        for b in range(2):
+            free[b].record(cur)
+        enqueue_copy(0)
+        out = None
+        for i in range(steps):
+            if i + 1 < steps:
+                enqueue_copy(i + 1)
+            cur.wait_event(ready[i % 2])
+            out = step(bufs[i % 2], True)       # float(loss) + packed.cpu(): device -> host every step
+            free[i % 2].record(cur)
+        return out
+
+    e2e_run(2)
+    ms_e2e = timed(lambda: e2e_run(args.steps), 1)
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -313,6 +344,7 @@ def run_gpu_arm(args):
         "config": {"workload": args.workload, "robot": w["robot"], "envs_per_gpu": bs, "substeps_per_window": window,
                    "frame_stride": stride, "bodies": nb, "dofs": nqd, "contacts_per_env": rm.nc,
                    "parallelism": "env-sharded x%d, 1 all-reduce of %d floats/step" % (world, 2 * nqd + nb),
+                   "params": "per-env replicated" if args.replicate_params else "shared (un-replicated)",
                    "l2": "working set >> 126 MB L2 (state checkpoint %.2f GB/step streamed once each way)"
                          % (env.workspace_bytes(bs, nsteps) / 1e9)},
         "gpu_launches": int(launches),
@@ -326,7 +358,8 @@ def run_gpu_arm(args):
                      "note": "the path is FP32-issue / latency bound, not HBM bound (SURVEY.md 8d)"},
         "e2e": {"value": env_steps / (ms_e2e / args.steps * 1e-3), "unit": "env-steps/s",
                 "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 4 + 4 * (2 * nqd + nb),
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "note": "pinned-host inputs, copy of step i+1 overlapped with the kernels of step i"},
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
@@ -344,6 +377,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--replicate-params", action="store_true",
+                    help="pass target_ke/kd, mass, inertia replicated per env like dp_model.py:723-730")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -87,17 +87,22 @@ int ppr_fk_backward(ppr_model_t m, int64_t n, const float* joint_q, const float*
  */
 size_t ppr_rollout_workspace_bytes(ppr_model_t m, int64_t bs, int64_t nsteps);
 
+/* shared_params = 0: target_ke/kd, body_inv_mass, body_inertia, body_inv_inertia are per-env replicated exactly as
+ * the reference passes them (dp_model.py:723-730).  shared_params = 1: they are ONE copy shared by all envs
+ * ([nqd], [nqd], [nb], [nb,3,3], [nb,3,3]) -- what the reference's replication encodes; the adjoint outputs stay
+ * per-env (the caller sums them, which is the backward of the replication). */
 int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t frame_stride, float dt,
+                        int32_t shared_params,
                         const float* q_init,          /* [bs*nq] */
                         const float* qd_init,         /* [bs*nqd] */
                         const float* torques,         /* [T, bs*nqd] or NULL */
                         const float* res_f,           /* [T, bs*nb, 6] or NULL */
                         const float* refs,            /* [T, bs*nqd] */
-                        const float* target_ke,       /* [bs*nqd] */
-                        const float* target_kd,       /* [bs*nqd] */
-                        const float* body_inv_mass,   /* [bs*nb] */
-                        const float* body_inertia,    /* [bs*nb,3,3] */
-                        const float* body_inv_inertia,/* [bs*nb,3,3] */
+                        const float* target_ke,       /* [bs*nqd]      ([nqd] if shared_params) */
+                        const float* target_kd,       /* [bs*nqd]      ([nqd]) */
+                        const float* body_inv_mass,   /* [bs*nb]       ([nb]) */
+                        const float* body_inertia,    /* [bs*nb,3,3]   ([nb,3,3]) */
+                        const float* body_inv_inertia,/* [bs*nb,3,3]   ([nb,3,3]) */
                         float* out_pos,               /* [F, bs*nb, 7] */
                         float* out_vel,               /* [F, bs*nb, 6] */
                         float* out_grf,               /* [F, bs*nb, 6] or NULL */
@@ -108,6 +113,7 @@ int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t frame
  * adj_body_mass of the reference is identically zero (integrate_bodies never uses `m`,
  * integrator_euler.py:43) and is therefore not an output here. */
 int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t frame_stride, float dt,
+                         int32_t shared_params,
                          const float* q_init, const float* qd_init, const float* torques, const float* res_f,
                          const float* refs, const float* target_ke, const float* target_kd,
                          const float* body_inv_mass, const float* body_inertia, const float* body_inv_inertia,

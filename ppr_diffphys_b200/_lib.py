@@ -37,8 +37,8 @@ def _declare(lib):
     lib.ppr_fk_backward.argtypes = [_vp, _i64] + [_vp] * 7
     lib.ppr_rollout_workspace_bytes.restype = C.c_size_t
     lib.ppr_rollout_workspace_bytes.argtypes = [_vp, _i64, _i64]
-    lib.ppr_rollout_forward.argtypes = [_vp, _i64, _i64, _i64, _f32] + [_vp] * 14 + [_vp, C.c_size_t, _vp]
-    lib.ppr_rollout_backward.argtypes = [_vp, _i64, _i64, _i64, _f32] + [_vp] * 22 + [_vp, C.c_size_t, _vp]
+    lib.ppr_rollout_forward.argtypes = [_vp, _i64, _i64, _i64, _f32, C.c_int32] + [_vp] * 14 + [_vp, C.c_size_t, _vp]
+    lib.ppr_rollout_backward.argtypes = [_vp, _i64, _i64, _i64, _f32, C.c_int32] + [_vp] * 22 + [_vp, C.c_size_t, _vp]
     lib.ppr_launch_count.restype = C.c_int64
     lib.ppr_launch_count.argtypes = []
     for name in EXPORTS:

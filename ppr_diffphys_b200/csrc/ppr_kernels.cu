@@ -447,6 +447,7 @@ fk_backward_kernel(DevModel M, int64_t n, const float* __restrict__ q, const flo
 struct RolloutArgs {
     int64_t bs, nsteps, stride, nwarps;
     float dt;
+    int pstride;  // 1: per-env parameter arrays, 0: one shared copy
     const float *q_init, *qd_init, *torques, *res_f, *refs, *ke, *kd, *inv_m, *I, *inv_I;
     float *out_pos, *out_vel, *out_grf, *out_jaf;
     float* ckpt;
@@ -536,15 +537,16 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     LaneInfo L = lane_setup(M, warp, lane, A.bs);
     // per-env parameters of this body / joint -> shared memory
     int64_t eb = (int64_t)L.env * M.nb + L.body;
-    par[0] = A.inv_m[eb];
+    int64_t ebp = (int64_t)L.env * A.pstride * M.nb + L.body;
+    par[0] = A.inv_m[ebp];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { par[(1 + i) * PPR_BLOCK] = A.I[eb * 9 + i]; par[(10 + i) * PPR_BLOCK] = A.inv_I[eb * 9 + i]; }
+    for (int i = 0; i < 9; ++i) { par[(1 + i) * PPR_BLOCK] = A.I[ebp * 9 + i]; par[(10 + i) * PPR_BLOCK] = A.inv_I[ebp * 9 + i]; }
     JointCtl<float> ctl;
     float ke[3], kd[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         bool use = L.type != JT_FREE && k < L.ndof;
-        int64_t d = (int64_t)L.env * M.nqd + L.qds + k;
+        int64_t d = (int64_t)L.env * A.pstride * M.nqd + L.qds + k;
         ke[k] = use ? A.ke[d] : 0.f; kd[k] = use ? A.kd[d] : 0.f;
         float4 lm = use ? M.lim[L.qds + k] : make_float4(-1e30f, 1e30f, 0.f, 0.f);
         ctl.lo[k] = lm.x; ctl.hi[k] = lm.y; ctl.lke[k] = lm.z; ctl.lkd[k] = lm.w;
@@ -620,9 +622,10 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     if (M.nc > 0) cm0 = load_mat(M, 0);
     LaneInfo L = lane_setup(M, warp, lane, A.bs);
     int64_t eb = (int64_t)L.env * M.nb + L.body;
-    par[0] = A.inv_m[eb];
+    int64_t ebp = (int64_t)L.env * A.pstride * M.nb + L.body;
+    par[0] = A.inv_m[ebp];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { par[(1 + i) * PPR_BLOCK] = A.I[eb * 9 + i]; par[(10 + i) * PPR_BLOCK] = A.inv_I[eb * 9 + i]; }
+    for (int i = 0; i < 9; ++i) { par[(1 + i) * PPR_BLOCK] = A.I[ebp * 9 + i]; par[(10 + i) * PPR_BLOCK] = A.inv_I[ebp * 9 + i]; }
 #pragma unroll
     for (int i = 0; i < 18; ++i) acc[i * PPR_BLOCK] = 0.f;
     JointCtl<float> ctl;
@@ -631,7 +634,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         bool use = jon && k < L.ndof;
-        int64_t d = (int64_t)L.env * M.nqd + L.qds + k;
+        int64_t d = (int64_t)L.env * A.pstride * M.nqd + L.qds + k;
         ke[k] = use ? A.ke[d] : 0.f; kd[k] = use ? A.kd[d] : 0.f;
         float4 lm = use ? M.lim[L.qds + k] : make_float4(-1e30f, 1e30f, 0.f, 0.f);
         ctl.lo[k] = lm.x; ctl.hi[k] = lm.y; ctl.lke[k] = lm.z; ctl.lkd[k] = lm.w;
@@ -967,7 +970,7 @@ extern "C" size_t ppr_rollout_workspace_bytes(ppr_model_t m, int64_t bs, int64_t
 }
 
 extern "C" int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t stride, float dt,
-                                   const float* q_init, const float* qd_init, const float* torques, const float* res_f,
+                                   int32_t shared_params, const float* q_init, const float* qd_init, const float* torques, const float* res_f,
                                    const float* refs, const float* ke, const float* kd, const float* inv_m,
                                    const float* I, const float* inv_I, float* out_pos, float* out_vel, float* out_grf,
                                    float* out_jaf, void* ws, size_t ws_bytes, void* stream) {
@@ -980,6 +983,7 @@ extern "C" int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, in
     RolloutArgs A;
     memset(&A, 0, sizeof(A));
     A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.nwarps = nwarps_for(m->d, bs); A.dt = dt;
+    A.pstride = shared_params ? 0 : 1;
     A.q_init = q_init; A.qd_init = qd_init; A.torques = torques; A.res_f = res_f; A.refs = refs; A.ke = ke; A.kd = kd;
     A.inv_m = inv_m; A.I = I; A.inv_I = inv_I;
     A.out_pos = out_pos; A.out_vel = out_vel; A.out_grf = out_grf; A.out_jaf = out_jaf; A.ckpt = (float*)ws;
@@ -993,7 +997,7 @@ extern "C" int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, in
 }
 
 extern "C" int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t stride, float dt,
-                                    const float* q_init, const float* qd_init, const float* torques,
+                                    int32_t shared_params, const float* q_init, const float* qd_init, const float* torques,
                                     const float* res_f, const float* refs, const float* ke, const float* kd,
                                     const float* inv_m, const float* I, const float* inv_I, const float* adj_pos,
                                     const float* adj_vel, float* adj_q_init, float* adj_qd_init, float* adj_torques,
@@ -1009,6 +1013,7 @@ extern "C" int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, i
     RolloutArgs A;
     memset(&A, 0, sizeof(A));
     A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.nwarps = nwarps_for(m->d, bs); A.dt = dt;
+    A.pstride = shared_params ? 0 : 1;
     A.q_init = q_init; A.qd_init = qd_init; A.torques = torques; A.res_f = res_f; A.refs = refs; A.ke = ke; A.kd = kd;
     A.inv_m = inv_m; A.I = I; A.inv_I = inv_I; A.ckpt = (float*)ws;
     A.adj_pos = adj_pos; A.adj_vel = adj_vel; A.adj_q_init = adj_q_init; A.adj_qd_init = adj_qd_init;

@@ -1,0 +1,298 @@
+"""Motion-imitation optimisation model on top of the B200 rollout ops -- the caller of the hot path.
+
+A compact host-side mirror of the reference's ``phys_model`` (/root/reference/diffphys/dp_model.py:56-1011): same
+method names and data flow for the part that feeds and consumes the simulator boundary,
+
+    preset_data (:407-427)  reinit_envs (:354-405)  compute_frame_start (:581-586)  get_batch_input (:611-662)
+    forward (:664-838)      backward (:840)         update (:511-516)
+
+and the same learnable quantities (control-reference networks, PD gains, body mass, global SE(3), initial velocity).
+What is deliberately NOT mirrored (out of the hot-path scope): visualiser / ``query()`` mesh
+articulation, lab4d coupling, in-memory checkpoint roll-back, per-parameter median gradient clipping.
+Differences that matter for speed: mocap interpolation runs in torch on the device (the reference calls scipy on
+the CPU every step, :605-609); shared parameters are passed UN-replicated to ``ForwardWarp`` (the reference
+replicates + inverts bs*nb 3x3 matrices per step, :723-730).
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .model import ASSET_DIR, load_robot
+from .ops import ForwardKinematics, ForwardWarp, SimEnv, convert_ppr_warp
+
+
+# ----------------------------------------------------------------------------------------- geometry (torch, xyzw)
+def quat_to_matrix(q):
+    x, y, z, w = q.unbind(-1)
+    n = (q * q).sum(-1)
+    s = 2.0 / n
+    return torch.stack([1 - s * (y * y + z * z), s * (x * y - z * w), s * (x * z + y * w),
+                        s * (x * y + z * w), 1 - s * (x * x + z * z), s * (y * z - x * w),
+                        s * (x * z - y * w), s * (y * z + x * w), 1 - s * (x * x + y * y)], -1).reshape(q.shape[:-1] + (3, 3))
+
+
+def quat_mul(a, b):
+    ax, ay, az, aw = a.unbind(-1)
+    bx, by, bz, bw = b.unbind(-1)
+    return torch.stack([aw * bx + bw * ax + ay * bz - az * by, aw * by + bw * ay + az * bx - ax * bz,
+                        aw * bz + bw * az + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz], -1)
+
+
+def axis_angle_to_quat(v):
+    ang = v.norm(dim=-1, keepdim=True)
+    half = 0.5 * ang
+    k = torch.where(ang > 1e-6, torch.sin(half) / ang.clamp_min(1e-6), 0.5 - ang * ang / 48.0)
+    return torch.cat([v * k, torch.cos(half)], -1)
+
+
+def rot_angle(mat, eps=1e-4):
+    """geom_utils.py:37-46"""
+    cos = (mat[..., 0, 0] + mat[..., 1, 1] + mat[..., 2, 2] - 1) / 2
+    return torch.acos(cos.clamp(-1 + eps, 1 - eps))
+
+
+def se3_loss(pred, gt, rot_ratio=0.1):
+    """dp_utils.py:113-138 for (...,7) poses (xyzw) or (...,6) twists."""
+    nan = torch.logical_or(pred.sum(-1).isnan(), gt.sum(-1).isnan())
+    trn = (pred[..., :3] - gt[..., :3]).pow(2).sum(-1)
+    if pred.shape[-1] == 7:
+        rot = rot_angle(quat_to_matrix(pred[..., 3:]) @ quat_to_matrix(gt[..., 3:]).transpose(-1, -2))
+    else:
+        rot = rot_angle(quat_to_matrix(axis_angle_to_quat(pred[..., 3:])) @
+                        quat_to_matrix(axis_angle_to_quat(gt[..., 3:])).transpose(-1, -2))
+    loss = trn + rot * rot_ratio
+    return torch.where(nan, torch.zeros_like(loss), loss)
+
+
+def reduce_loss(loss_seq):
+    """dp_utils.py:93-110 without the trajectory clipping branch."""
+    pos = loss_seq > 0
+    return loss_seq[pos].mean() if bool(pos.any()) else loss_seq.mean()
+
+
+def rotate_frame(global_q, q):
+    """T = T_global @ T  (dp_utils.py:60-72) on (...,7) poses."""
+    R = quat_to_matrix(global_q[3:7])
+    pos = q[..., :3] @ R.T + global_q[:3]
+    return torch.cat([pos, quat_mul(global_q[3:7].expand_as(q[..., 3:7]), q[..., 3:7])], -1)
+
+
+def rotate_frame_vel(global_q, qd):
+    R = quat_to_matrix(global_q[3:7])
+    return torch.cat([qd[..., :3] @ R.T, qd[..., 3:6] @ R.T], -1)
+
+
+def compose_delta(q, delta):
+    """dp_utils.py:21-30: T = T_delta @ T with delta = (translation, axis-angle)."""
+    dq = axis_angle_to_quat(delta[..., 3:6])
+    R = quat_to_matrix(dq)
+    pos = (R @ q[..., :3, None])[..., 0] + delta[..., :3]
+    return torch.cat([pos, quat_mul(dq, q[..., 3:7])], -1)
+
+
+class TimeMLP(nn.Module):
+    """Scalar-time -> vector network (Fourier time embedding + MLP + scaled head); stands in for the reference's
+    TimeMLPWrapper (torch_utils.py:116-190). The last layer starts at zero so every predicted delta starts at 0."""
+
+    def __init__(self, num_frames, out_channels, num_freq=6, width=128, depth=3, time_scale=1.0, output_scale=1.0):
+        super().__init__()
+        self.num_frames, self.time_scale, self.output_scale = num_frames, time_scale, output_scale
+        self.register_buffer("freqs", 2.0 ** torch.arange(num_freq, dtype=torch.float32) * math.pi)
+        layers, d = [], 2 * num_freq + 1
+        for _ in range(depth):
+            layers += [nn.Linear(d, width), nn.ReLU(True)]
+            d = width
+        self.body = nn.Sequential(*layers)
+        self.head = nn.Linear(width, out_channels)
+        nn.init.zeros_(self.head.weight)
+        nn.init.zeros_(self.head.bias)
+
+    def forward(self, frame_id):
+        t = (frame_id.float() / self.num_frames * 2 - 1)[..., None] * self.time_scale
+        emb = torch.cat([t, torch.sin(t * self.freqs), torch.cos(t * self.freqs)], -1)
+        return self.head(self.body(emb)) * self.output_scale
+
+
+def load_motion(seqname):
+    z = np.load(os.path.join(ASSET_DIR, "motion_%s.npz" % seqname))
+    return z["frames"].astype(np.float32), float(z["frame_duration"])
+
+
+def parse_amp(amp):
+    """dataloader.py:21-31 column map."""
+    return dict(pos=amp[..., 0:3], orn=amp[..., 3:7], vel=amp[..., 31:34], avel=amp[..., 34:37],
+                jang=amp[..., 7:19], jvel=amp[..., 37:49])
+
+
+_BULLET2GL = torch.tensor([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [1.0, 0.0, 0.0]])
+
+
+class ImitationModel(nn.Module):
+    def __init__(self, robot="laikago", seqname="mi-trot", dt=5e-4, device="cuda", total_iters=101, lr=1e-4,
+                 traj_wt=0.01, pos_state_wt=0.01, vel_state_wt=1e-4, noise_std=2e-3, seed=0):
+        super().__init__()
+        self.device = torch.device(device)
+        self.dt, self.noise_std = dt, noise_std
+        self.wts = dict(traj=traj_wt, pos_state=pos_state_wt, vel_state=vel_state_wt)
+        self.rng = np.random.RandomState(seed)
+        self.robot_model = load_robot(robot)
+        rm = self.robot_model
+        self.n_dof, self.n_links = rm.nqd - 6, rm.nb
+        frames, self.frame_interval = load_motion(seqname)
+        self.preset_data(frames)
+        self.env = SimEnv(rm, device=self.device)
+        self.target_ke = nn.Parameter(torch.as_tensor(rm.joint_target_ke))
+        self.target_kd = nn.Parameter(torch.as_tensor(rm.joint_target_kd))
+        self.body_mass = nn.Parameter(torch.as_tensor(rm.body_mass))
+        self.register_buffer("norm_body_inertia", torch.as_tensor(rm.norm_body_inertia))
+        N = self.total_frames
+        self.root_pose_mlp = TimeMLP(N, 6, time_scale=0.1, output_scale=0.5)
+        self.joint_angle_mlp = TimeMLP(N, self.n_dof)
+        self.vel_mlp = TimeMLP(N, 6 + self.n_dof, output_scale=5.0)
+        self.global_q = nn.Parameter(torch.tensor([0.0, 0, 0, 0, 0, 0, 1.0]))
+        self.to(self.device)
+        self.init_global_q()
+        self.progress = 0.0
+        explicit = [self.global_q, self.target_ke, self.target_kd, self.body_mass]
+        nets = [p for m in (self.root_pose_mlp, self.joint_angle_mlp, self.vel_mlp) for p in m.parameters()]
+        self.optimizer = torch.optim.AdamW([{"params": explicit, "lr": lr * 10}, {"params": nets, "lr": lr}],
+                                           weight_decay=1e-4)
+        total = max(2, total_iters)
+        self.scheduler = torch.optim.lr_scheduler.OneCycleLR(self.optimizer, [lr * 10, lr], total, pct_start=2.0 / total,
+                                                             cycle_momentum=False, anneal_strategy="linear",
+                                                             final_div_factor=1e2, div_factor=25)
+
+    # ---- data ----------------------------------------------------------------------------------------
+    def preset_data(self, frames):
+        self.total_frames = frames.shape[0]
+        self.steps_per_fr_interval = int(self.frame_interval / self.dt)
+        self.register_buffer("amp_info", torch.as_tensor(frames))
+
+    def get_mocap_data(self, steps_fr):
+        """linear interpolation / extrapolation of all columns at fractional frame ids (dp_model.py:421-427),
+        then bullet2gl (dp_utils.py:141-156, in_bullet = False)."""
+        f0 = steps_fr.floor().clamp(0, self.total_frames - 2).long()
+        w = (steps_fr - f0.float())[..., None]
+        amp = self.amp_info[f0] * (1 - w) + self.amp_info[f0 + 1] * w
+        m = parse_amp(amp)
+        P = _BULLET2GL.to(amp.device)
+        out = dict(jang=m["jang"], jvel=m["jvel"])
+        out["pos"] = m["pos"] @ P.T
+        out["orn"] = torch.cat([m["orn"][..., :3] @ P.T, m["orn"][..., 3:]], -1)
+        out["vel"] = m["vel"] @ P.T
+        out["avel"] = m["avel"] @ P.T
+        return out
+
+    def lowest_point(self, body_q):
+        """min world-y over the collision vertices (stands in for get_foot_height's mesh query, :574-579)."""
+        rm = self.robot_model
+        cb = torch.as_tensor(rm.contact_body, dtype=torch.long, device=body_q.device)
+        cp = torch.as_tensor(rm.contact_point, device=body_q.device)
+        R = quat_to_matrix(body_q[..., cb, 3:7])
+        y = (R @ cp[:, :, None])[..., 1, 0] + body_q[..., cb, 1]
+        return y.min(-1)[0]
+
+    @torch.no_grad()
+    def init_global_q(self):
+        """ground-align the clip: lowest collision vertex of frame 0 touches y = 0 (dp_model.py:243-267)."""
+        m = self.get_mocap_data(torch.zeros(1, 1, device=self.device))
+        q = torch.cat([m["pos"], m["orn"], m["jang"]], -1)  # 1,1,nq
+        qd = torch.zeros(1, 1, self.env.nqd, device=self.device)
+        bq, _, _ = ForwardKinematics.apply(q, qd, self.env)
+        self.global_q.data[1] = -self.lowest_point(bq)[0, 0]
+
+    def reinit_envs(self, num_envs, frames_per_wdw, is_eval=False):
+        self.num_envs, self.frames_per_wdw = num_envs, frames_per_wdw
+        spf = self.steps_per_fr_interval
+        self.steps_idx = range(spf * (frames_per_wdw - 1) + 1)
+        self.steps_idx_fr = torch.arange(len(self.steps_idx), device=self.device).float() / spf
+        self.frame2step = [i for i in self.steps_idx if i % spf == 0]
+        self.is_eval = is_eval
+
+    def compute_frame_start(self):
+        fs = self.rng.rand(self.num_envs) * (self.total_frames - self.frames_per_wdw)
+        return torch.as_tensor(np.round(fs), device=self.device, dtype=torch.float32)
+
+    def fk_pos_vel(self, q, ja, qd, jad):
+        """(bs,F,..) targets -> body poses / twists through ForwardKinematics (dp_model.py:588-603)."""
+        tq = torch.cat([q, ja], -1).permute(1, 0, 2).contiguous()
+        tqd = convert_ppr_warp(torch.cat([qd, jad], -1).permute(1, 0, 2).contiguous())
+        bq, bqd, frames = ForwardKinematics.apply(tq, tqd, self.env)
+        return bq, convert_ppr_warp(bqd), frames
+
+    def get_batch_input(self, steps_fr):
+        msm = self.get_mocap_data(steps_fr)
+        target_q = rotate_frame(self.global_q, torch.cat([msm["pos"], msm["orn"]], -1))      # bs,T,7
+        target_qd = rotate_frame_vel(self.global_q, torch.cat([msm["vel"], msm["avel"]], -1))  # bs,T,6
+        f2s = self.frame2step
+        target_position, _, self.target_trajs = self.fk_pos_vel(target_q[:, f2s], msm["jang"][:, f2s],
+                                                                target_qd[:, f2s], msm["jvel"][:, f2s])
+        fid = steps_fr.reshape(-1)
+        bs, T = steps_fr.shape
+        delta_root = self.root_pose_mlp(fid).view(bs, T, 6)
+        delta_ja = self.joint_angle_mlp(fid).view(bs, T, -1)
+        queried_qd = self.vel_mlp(fid).view(bs, T, -1)
+        queried_q = compose_delta(target_q, delta_root)
+        queried_ja = msm["jang"] + delta_ja
+        # time-major flattening (rearrange_pred, :555-572)
+        q_all = torch.cat([queried_q, queried_ja], -1).permute(1, 0, 2).reshape(T, -1)
+        qd_all = queried_qd.permute(1, 0, 2).reshape(T, -1)
+        ref_ja = torch.cat([torch.zeros_like(queried_ja[..., :6]), queried_ja], -1).permute(1, 0, 2).reshape(T, -1)
+        return target_position, ref_ja, q_all, qd_all
+
+    # ---- one optimisation step -------------------------------------------------------------------------
+    def forward(self, frame_start=None):
+        if frame_start is None:
+            frame_start = self.compute_frame_start()
+        steps_fr = frame_start[:, None] + self.steps_idx_fr[None]                     # bs,T
+        target_position, ref_ja, queried_q, queried_qd = self.get_batch_input(steps_fr)
+        bs, F = self.num_envs, self.frames_per_wdw
+        q_init = queried_q[0].reshape(-1)
+        if self.training and self.noise_std > 0 and not self.is_eval:                 # dp_model.py:700-712
+            ratio = float(np.clip(1 - 1.5 * self.progress, 0, 1))
+            noise = torch.as_tensor(self.rng.normal(size=(bs, self.env.nq), scale=self.noise_std * ratio),
+                                    device=self.device, dtype=torch.float32)
+            noise[:, :3] = 0
+            noise[:, 3:7] *= 5
+            q_init = q_init + noise.reshape(-1)
+        qd_init = convert_ppr_warp(queried_qd[0].view(bs, -1)).reshape(-1)
+        inv_m = 1.0 / self.body_mass
+        I = self.norm_body_inertia * self.body_mass[:, None, None]
+        sim_position, sim_velocity = ForwardWarp.apply(q_init, qd_init, None, None, ref_ja, self.target_ke,
+                                                       self.target_kd, self.body_mass, inv_m, I, torch.linalg.inv(I),
+                                                       self)
+        sim_velocity = convert_ppr_warp(sim_velocity)
+        f2s = self.frame2step
+        qq = queried_q[f2s].reshape(F, bs, -1)
+        qqd = convert_ppr_warp(queried_qd[f2s].reshape(F, bs, -1))
+        queried_position, queried_velocity, self.pid_ref = ForwardKinematics.apply(qq, qqd, self.env)
+        queried_velocity = convert_ppr_warp(queried_velocity)
+        sim_position = sim_position.reshape(F, bs, -1, 7).permute(1, 0, 2, 3)
+        sim_velocity = sim_velocity.reshape(F, bs, -1, 6).permute(1, 0, 2, 3)
+        loss_dict = {
+            "traj": reduce_loss(se3_loss(sim_position, target_position).mean(-1)),
+            "pos_state": reduce_loss(se3_loss(queried_position, sim_position.detach()).mean(-1)),
+            "vel_state": reduce_loss(se3_loss(queried_velocity, sim_velocity.detach()).mean(-1)),
+        }
+        total = sum(v * self.wts[k] for k, v in loss_dict.items())
+        out = {"loss_" + k: v for k, v in loss_dict.items()}
+        out["total_loss"] = total
+        return out
+
+    def backward(self, loss):
+        loss.backward()
+
+    def update(self, thresh=10.0):
+        params = [p for g in self.optimizer.param_groups for p in g["params"] if p.grad is not None]
+        grad_norm = torch.nn.utils.clip_grad_norm_(params, thresh)
+        if not torch.isfinite(grad_norm) or grad_norm > thresh:   # check_grad (:936-963) without the roll-back
+            self.optimizer.zero_grad()
+        self.optimizer.step()
+        self.scheduler.step()
+        self.optimizer.zero_grad()
+        return {"grad_norm": float(grad_norm)}

@@ -152,7 +152,7 @@ class SimEnv:
         return int(self._lib.ppr_rollout_workspace_bytes(self._h, bs, nsteps))
 
     def rollout_forward(self, bs, nsteps, stride, dt, q_init, qd_init, torques, res_f, refs, ke, kd, inv_m, I, inv_I,
-                        want_forces=True, workspace=None):
+                        want_forces=True, workspace=None, shared_params=False):
         F = (nsteps - 1) // stride + 1
         dev = self.device
         pos = torch.empty(F, bs * self.nb, 7, device=dev, dtype=torch.float32)
@@ -164,13 +164,14 @@ class SimEnv:
             workspace = torch.empty((nbytes + 3) // 4, device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             _lib.check(self._lib.ppr_rollout_forward(
-                self._h, bs, nsteps, stride, C.c_float(dt), _ptr(q_init), _ptr(qd_init), _ptr(torques), _ptr(res_f),
+                self._h, bs, nsteps, stride, C.c_float(dt), int(bool(shared_params)), _ptr(q_init), _ptr(qd_init),
+                _ptr(torques), _ptr(res_f),
                 _ptr(refs), _ptr(ke), _ptr(kd), _ptr(inv_m), _ptr(I), _ptr(inv_I), _ptr(pos), _ptr(vel), _ptr(grf),
                 _ptr(jaf), _ptr(workspace), C.c_size_t(workspace.numel() * 4), _stream()), "ppr_rollout_forward")
         return pos, vel, grf, jaf, workspace
 
     def rollout_backward(self, bs, nsteps, stride, dt, q_init, qd_init, torques, res_f, refs, ke, kd, inv_m, I, inv_I,
-                         adj_pos, adj_vel, workspace):
+                         adj_pos, adj_vel, workspace, shared_params=False):
         dev = self.device
         e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
         g = dict(q_init=e(bs * self.nq), qd_init=e(bs * self.nqd),
@@ -181,7 +182,8 @@ class SimEnv:
                  body_inv_inertia=e(bs * self.nb, 3, 3))
         with torch.cuda.device(dev):
             _lib.check(self._lib.ppr_rollout_backward(
-                self._h, bs, nsteps, stride, C.c_float(dt), _ptr(q_init), _ptr(qd_init), _ptr(torques), _ptr(res_f),
+                self._h, bs, nsteps, stride, C.c_float(dt), int(bool(shared_params)), _ptr(q_init), _ptr(qd_init),
+                _ptr(torques), _ptr(res_f),
                 _ptr(refs), _ptr(ke), _ptr(kd), _ptr(inv_m), _ptr(I), _ptr(inv_I), _ptr(adj_pos), _ptr(adj_vel),
                 _ptr(g["q_init"]), _ptr(g["qd_init"]), _ptr(g["torques"]), _ptr(g["res_f"]), _ptr(g["refs"]),
                 _ptr(g["target_ke"]), _ptr(g["target_kd"]), _ptr(g["body_inv_mass"]), _ptr(g["body_inertia"]),
@@ -259,10 +261,22 @@ class ForwardWarp(torch.autograd.Function):
                  inv_m=_f32c(body_inv_mass, dev), I=_f32c(body_inertia, dev), inv_I=_f32c(body_inv_inertia, dev))
         assert a["q_init"].numel() == bs * env.nq and a["qd_init"].numel() == bs * env.nqd
         assert a["refs"].numel() == nsteps * bs * env.nqd
+        # Extension of the reference signature: the five parameter tensors may be given UN-replicated
+        # ([nqd], [nqd], [nb], [nb,3,3], [nb,3,3]); the kernels then read one shared copy and the returned
+        # gradients are summed over envs (= the backward of dp_model.py:723-725's repeat()).
+        per_env = dict(ke=bs * env.nqd, kd=bs * env.nqd, inv_m=bs * env.nb, I=bs * env.nb * 9, inv_I=bs * env.nb * 9)
+        shared = all(a[k].numel() * bs == n for k, n in per_env.items()) and bs > 1
+        if not shared:
+            for k, n in per_env.items():
+                if a[k].numel() * bs == n and bs > 1:  # mixed: replicate the shared ones
+                    a[k] = a[k].reshape(1, -1).expand(bs, -1).reshape(-1).contiguous()
+                assert a[k].numel() == n, "bad size for %s" % k
         want_forces = bool(getattr(self, "record_forces", True))
         pos, vel, grf, jaf, ws = env.rollout_forward(bs, nsteps, stride, float(self.dt), a["q_init"], a["qd_init"],
                                                      a["torques"], a["res_f"], a["refs"], a["ke"], a["kd"],
-                                                     a["inv_m"], a["I"], a["inv_I"], want_forces=want_forces)
+                                                     a["inv_m"], a["I"], a["inv_I"], want_forces=want_forces,
+                                                     shared_params=shared)
+        ctx.shared = shared
         F = pos.shape[0]
         self.grfs = [grf[i] for i in range(F)] if want_forces else []
         self.jafs = [jaf[i] for i in range(F)] if want_forces else []
@@ -281,9 +295,17 @@ class ForwardWarp(torch.autograd.Function):
         bs, nsteps, stride, dt = ctx.dims
         g = env.rollout_backward(bs, nsteps, stride, dt, a["q_init"], a["qd_init"], a["torques"], a["res_f"],
                                  a["refs"], a["ke"], a["kd"], a["inv_m"], a["I"], a["inv_I"],
-                                 _f32c(adj_body_qs, env.device), _f32c(adj_body_qd, env.device), ctx.ws)
+                                 _f32c(adj_body_qs, env.device), _f32c(adj_body_qd, env.device), ctx.ws,
+                                 shared_params=ctx.shared)
         need, sh = ctx.needs_input_grad, ctx.shapes
-        pick = lambda i, t, shape: _scrub(t).view(shape) if (need[i] and t is not None) else None
+
+        def pick(i, t, shape):
+            if not need[i] or t is None:
+                return None
+            t = _scrub(t)
+            if t.numel() != int(np.prod(shape)):  # un-replicated parameter: sum the per-env gradients
+                t = t.view(bs, -1).sum(0)
+            return t.view(shape)
         body_mass_grad = torch.zeros(sh["mass"], device=env.device) if need[7] else None  # K5 never reads m
         return (pick(0, g["q_init"], sh["q_init"]), pick(1, g["qd_init"], sh["qd_init"]),
                 pick(2, g["torques"], sh["torques"]), pick(3, g["res_f"], sh["res_f"]),

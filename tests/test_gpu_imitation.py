@@ -1,0 +1,49 @@
+"""End-to-end use of the drop-in ops by their caller: the motion-imitation loop of the reference's run.sh recipe
+(laikago, mocap clip, windows of frames) must reduce the trajectory loss (README.md:39-47 is the reference's only
+behavioural claim), with finite gradients reaching every learnable quantity named by the north star: control
+reference nets, PD gains, body mass, global SE(3), initial velocity."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_imitation_loss_decreases_and_all_parameters_get_gradients():
+    from ppr_diffphys_b200.imitation import ImitationModel
+    torch.manual_seed(8)
+    iters = 40
+    model = ImitationModel("laikago", "mi-trot", total_iters=iters, lr=1e-4, seed=0)
+    model.record_forces = False
+    model.train()
+    model.reinit_envs(8, 6)   # 8 windows x 6 frames (166 substeps)
+    fs = torch.linspace(0, model.total_frames - 6, 8, device=model.device).round()
+    first = last = None
+    for it in range(iters):
+        model.progress = it / iters
+        out = model(frame_start=fs)
+        model.backward(out["total_loss"])
+        if it == 0:
+            for name in ("target_ke", "target_kd", "body_mass", "global_q"):
+                g = getattr(model, name).grad
+                assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0, name
+            for net in (model.root_pose_mlp, model.joint_angle_mlp, model.vel_mlp):
+                g = net.head.weight.grad
+                assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
+            first = float(out["loss_traj"].detach())
+        model.update()
+        last = float(out["loss_traj"].detach())
+        assert last == last  # not NaN
+    assert last < first, (first, last)
+
+
+def test_eval_rollout_side_channels():
+    from ppr_diffphys_b200.imitation import ImitationModel
+    model = ImitationModel("laikago", "mi-pace", total_iters=2)
+    model.eval()
+    model.reinit_envs(1, model.total_frames, is_eval=True)   # the reference's eval shape: 1 env x all 39 frames
+    with torch.no_grad():
+        out = model()
+    F = model.total_frames
+    assert len(model.steps_idx) == 33 * (F - 1) + 1
+    assert len(model.grfs) == F and model.grfs[0].shape == (13, 6) and len(model.sim_trajs) == F
+    assert model.sim_trajs[0].shape == (13, 7) and torch.isfinite(out["total_loss"])

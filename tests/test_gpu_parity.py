@@ -246,6 +246,44 @@ def test_zero_forces_equal_null_pointers():
     assert float(a0["refs"].grad.view(T, bs, -1)[..., :6].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("robot", ["laikago", "human"])
+def test_shared_parameters_equal_replicated(robot):
+    """Un-replicated [nqd]/[nb]/[nb,3,3] parameters == the reference's per-env replication (dp_model.py:723-730):
+    bit-identical trajectories, and gradients equal to the sum over envs of the per-env gradients."""
+    from ppr_diffphys_b200 import ForwardWarp, SimEnv, load_robot
+    stride, F, bs = 16, 3, 6
+    T = stride * (F - 1) + 1
+    rm, d = make_inputs(robot, bs=bs, T=T, seed=12)
+    d = settle_height(rm, d, 0.002)
+    dev = torch.device("cuda:0")
+    env = SimEnv(rm)
+    ke = torch.as_tensor(rm.joint_target_ke, device=dev)
+    kd = torch.as_tensor(rm.joint_target_kd, device=dev)
+    mass = torch.as_tensor(rm.body_mass, device=dev) * 1.1
+    nI = torch.as_tensor(rm.norm_body_inertia, device=dev)
+    caller = Caller(env, bs, T, stride)
+    base = dict(q=d["q_init"].float().reshape(-1).to(dev), qd=d["qd_init"].float().reshape(-1).to(dev),
+                refs=d["refs"].float().reshape(T, -1).to(dev))
+
+    def run(shared):
+        p = [x.clone().requires_grad_(True) for x in (ke, kd, 1.0 / mass, nI * mass[:, None, None],
+                                                      torch.linalg.inv(nI * mass[:, None, None]))]
+        if shared:
+            args = p
+        else:
+            args = [x[None].expand(bs, *x.shape).reshape(bs * x.shape[0], *x.shape[1:]) for x in p]
+        pos, vel = ForwardWarp.apply(base["q"], base["qd"], None, None, base["refs"], args[0], args[1],
+                                     mass if shared else mass.repeat(bs), args[2], args[3], args[4], caller)
+        ((pos ** 2).sum() + (vel ** 2).sum() * 0.1).backward()
+        return pos.detach(), [x.grad for x in p]
+
+    p0, g0 = run(False)
+    p1, g1 = run(True)
+    assert torch.equal(p0, p1)
+    for a, b in zip(g0, g1):
+        assert a.shape == b.shape and torch.allclose(a, b, rtol=1e-4, atol=1e-6 * float(a.abs().max()))
+
+
 def test_single_frame_window_and_single_env():
     from oracle import sim_oracle as so
     from ppr_diffphys_b200 import SimEnv
@@ -273,8 +311,8 @@ def test_c_abi_error_codes():
     x = torch.zeros(1024, device="cuda")
     p = C.c_void_p(x.data_ptr())
     args = [p] * 2 + [n, n] + [p] * 6 + [p, p, n, n]
-    assert lib.ppr_rollout_forward(h, 2, 65, 32, C.c_float(5e-4), *args, p, C.c_size_t(16), n) == -4  # workspace
-    assert lib.ppr_rollout_forward(h, 0, 65, 32, C.c_float(5e-4), *args, p, C.c_size_t(16), n) == 0   # empty batch
+    assert lib.ppr_rollout_forward(h, 2, 65, 32, C.c_float(5e-4), 0, *args, p, C.c_size_t(16), n) == -4  # workspace
+    assert lib.ppr_rollout_forward(h, 0, 65, 32, C.c_float(5e-4), 0, *args, p, C.c_size_t(16), n) == 0   # empty batch
     assert lib.ppr_rollout_workspace_bytes(h, 2, 65) == 1 * 65 * 24 * 32 * 4
     before = _lib.launch_count()
     env.fk(torch.zeros(3, env.nq, device="cuda"), torch.zeros(3, env.nqd, device="cuda"))
