@@ -262,7 +262,7 @@ def run_gpu_arm(args):
     inv_m, I, inv_I = mass_chain(mass, nI)
     ws = None
     evs = []
-    for i in range(args.steps + 1):
+    for i in range(max(args.steps, 5) + 1):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
         pos, vel, _, _, ws = env.rollout_forward(bs, nsteps, stride, DT, dev_inp["q_init"], dev_inp["qd_init"], None,
@@ -274,8 +274,9 @@ def run_gpu_arm(args):
         e[2].record()
         evs.append(e)
     torch.cuda.synchronize()
-    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in evs[1:]) / args.steps
-    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in evs[1:]) / args.steps
+    med = lambda v: sorted(v)[len(v) // 2]   # median: robust to a stray slow launch
+    fwd_ms = med([e[0].elapsed_time(e[1]) for e in evs[1:]])
+    bwd_ms = med([e[1].elapsed_time(e[2]) for e in evs[1:]])
     # ---- end-to-end: host (pinned) inputs -> device, step, loss + packed shared-parameter grads -> host.
     # Every step's inputs are copied inside the timed region; the copy of step i+1 is issued on a copy stream
     # (double-buffered device inputs) so that it overlaps the kernels of step i.

@@ -82,6 +82,15 @@ __device__ __forceinline__ BodyF shf_body(const BodyF& b, int src) {
 __device__ __forceinline__ WrenchF shf_wrench(const WrenchF& w, int src) {
     WrenchF o; o.t = shf3(w.t, src); o.f = shf3(w.f, src); return o;
 }
+// Ampere-style asynchronous global->shared copies (LDGSTS): the adjoint kernel streams the NEXT checkpoint row into
+// shared memory while it differentiates the current substep, so the ~700-cycle DRAM latency is never on the
+// critical path and no registers are held for the prefetched values.
+__device__ __forceinline__ void cp_async4(volatile float* smem_dst, const float* gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared((const void*)smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -524,12 +533,12 @@ template <int JM, bool LIMITS, bool QOFF>
 __global__ void __launch_bounds__(PPR_BLOCK, PPR_FWD_MINB)
 rollout_forward_kernel(DevModel M, RolloutArgs A) {
     __shared__ int clist_all[PPR_WARPS * 32 * PPR_CLIST_STRIDE];
-    __shared__ float sm_st[PPR_WARPS * PPR_NSTATIC * 32];
+    __shared__ float sm_st[PPR_NSTATIC * 32];  // per BLOCK: every warp stages the same per-body values
     __shared__ float sm_par[PPR_NPAR * PPR_BLOCK];
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     int* clist = clist_all + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
-    volatile float* st = sm_st + (threadIdx.x >> 5) * PPR_NSTATIC * 32;
+    volatile float* st = sm_st;
     volatile float* par = sm_par + threadIdx.x;
     if (warp >= A.nwarps) return;
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
@@ -608,15 +617,17 @@ template <int JM, bool LIMITS, bool QOFF>
 __global__ void __launch_bounds__(PPR_BLOCK, PPR_BWD_MINB)
 rollout_backward_kernel(DevModel M, RolloutArgs A) {
     __shared__ int clist_all[PPR_WARPS * 32 * PPR_CLIST_STRIDE];
-    __shared__ float sm_st[PPR_WARPS * PPR_NSTATIC * 32];
+    __shared__ float sm_st[PPR_NSTATIC * 32];  // per BLOCK: every warp stages the same per-body values
     __shared__ float sm_par[PPR_NPAR * PPR_BLOCK];
     __shared__ float sm_acc[18 * PPR_BLOCK];
+    __shared__ float sm_row[PPR_CKPT_FLOATS * PPR_BLOCK];  // the prefetched checkpoint row, [c][thread]
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     int* clist = clist_all + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
-    volatile float* st = sm_st + (threadIdx.x >> 5) * PPR_NSTATIC * 32;
+    volatile float* st = sm_st;
     volatile float* par = sm_par + threadIdx.x;
     volatile float* acc = sm_acc + threadIdx.x;
+    volatile float* row = sm_row + threadIdx.x;
     if (warp >= A.nwarps) return;
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
     if (M.nc > 0) cm0 = load_mat(M, 0);
@@ -677,19 +688,33 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         }
         if (t == 0) break;
         int64_t tp = t - 1;  // differentiate substep tp -> t
-        const float* c = ck + tp * ck_step;
+        if (t == last) {     // first row: nothing was prefetched yet
+            const float* c0 = ck + tp * ck_step;
+#pragma unroll
+            for (int i = 0; i < PPR_CKPT_FLOATS; ++i) cp_async4(row + i * PPR_BLOCK, c0 + i * 32);
+            cp_async_commit();
+        }
+        cp_async_wait_all();
         BodyF s;
         WrenchF F;
-        s.x = v3<float>(c[0 * 32], c[1 * 32], c[2 * 32]);
-        s.r = q4<float>(c[3 * 32], c[4 * 32], c[5 * 32], c[6 * 32]);
-        s.w = v3<float>(c[7 * 32], c[8 * 32], c[9 * 32]);
-        s.v = v3<float>(c[10 * 32], c[11 * 32], c[12 * 32]);
-        F.t = v3<float>(c[13 * 32], c[14 * 32], c[15 * 32]);
-        F.f = v3<float>(c[16 * 32], c[17 * 32], c[18 * 32]);
+        s.x = v3<float>(row[0 * PPR_BLOCK], row[1 * PPR_BLOCK], row[2 * PPR_BLOCK]);
+        s.r = q4<float>(row[3 * PPR_BLOCK], row[4 * PPR_BLOCK], row[5 * PPR_BLOCK], row[6 * PPR_BLOCK]);
+        s.w = v3<float>(row[7 * PPR_BLOCK], row[8 * PPR_BLOCK], row[9 * PPR_BLOCK]);
+        s.v = v3<float>(row[10 * PPR_BLOCK], row[11 * PPR_BLOCK], row[12 * PPR_BLOCK]);
+        F.t = v3<float>(row[13 * PPR_BLOCK], row[14 * PPR_BLOCK], row[15 * PPR_BLOCK]);
+        F.f = v3<float>(row[16 * PPR_BLOCK], row[17 * PPR_BLOCK], row[18 * PPR_BLOCK]);
         ContactRec rec;
-        rec.cnt = __float_as_uint(c[19 * 32]);
-        rec.lo = (unsigned long long)__float_as_uint(c[20 * 32]) | ((unsigned long long)__float_as_uint(c[21 * 32]) << 32);
-        rec.hi = (unsigned long long)__float_as_uint(c[22 * 32]) | ((unsigned long long)__float_as_uint(c[23 * 32]) << 32);
+        rec.cnt = __float_as_uint(row[19 * PPR_BLOCK]);
+        rec.lo = (unsigned long long)__float_as_uint(row[20 * PPR_BLOCK]) |
+                 ((unsigned long long)__float_as_uint(row[21 * PPR_BLOCK]) << 32);
+        rec.hi = (unsigned long long)__float_as_uint(row[22 * PPR_BLOCK]) |
+                 ((unsigned long long)__float_as_uint(row[23 * PPR_BLOCK]) << 32);
+        if (tp > 0) {  // every slot is private to its thread: safe to refill as soon as it has been read
+            const float* cn = ck + (tp - 1) * ck_step;
+#pragma unroll
+            for (int i = 0; i < PPR_CKPT_FLOATS; ++i) cp_async4(row + i * PPR_BLOCK, cn + i * 32);
+            cp_async_commit();
+        }
         const F3 com = st_vec3(st, ST_COM, L.body);
         F3 xc = s.x + qrot(s.r, com);
         load_ctl(M, L, A, tp, ke, kd, ctl);
