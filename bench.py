@@ -325,7 +325,9 @@ def run_gpu_arm(args):
     peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        if bs == w["bs"]:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload][
+                "rollout_backward_kernel"]
     except Exception:
         pass
     bwd_gbs = ab["bwd"] * bs * window / (bwd_ms * 1e-3) / 1e9
@@ -338,6 +340,22 @@ def run_gpu_arm(args):
             cpu = {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
         except Exception as ex:  # the checker is optional for the GPU arm
             cpu = {"value": None, "unit": "env-steps/s", "cores": None, "kind": "port", "sample": "failed: %r" % (ex,)}
+    others = None
+    if world == 1 and not args.no_extras and args.workload == DEFAULT_WORKLOAD and not args.envs:
+        # the remaining BASELINE.json configs (parity-test cases, not bench lines) for context: each in its own
+        # short process, device-resident step only
+        others = []
+        for wname in ("laikago-trot-64x760", "quad-1024x64", "human-4096x64-contact"):
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", wname, "--no-cpu",
+                                      "--no-extras", "--steps", "3", "--warmup", "3"], capture_output=True, text=True,
+                                     timeout=300).stdout.strip().splitlines()[-1]
+                d = json.loads(out)
+                others.append({"workload": wname, "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
+                               "kernels_ms": d["kernels_ms"], "roofline_frac_fwd_bwd": d["roofline"]["fwd_bwd_combined_frac"],
+                               "e2e": d["e2e"]["value"]})
+            except Exception as ex:
+                others.append({"workload": wname, "error": repr(ex)})
     line = {
         "metric": "env_steps_per_sec_fwd_bwd", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -363,6 +381,7 @@ def run_gpu_arm(args):
                 "note": "pinned-host inputs, copy of step i+1 overlapped with the kernels of step i"},
         "cpu_baseline": cpu,
         "clocks": clocks,
+        "other_configs": others,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -378,6 +397,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other_configs context measurements")
     ap.add_argument("--replicate-params", action="store_true",
                     help="pass target_ke/kd, mass, inertia replicated per env like dp_model.py:723-730")
     args = ap.parse_args()
