@@ -276,10 +276,12 @@ PPR_UNROLL
         t_out = clamp3(t, T(1e4));
         f_out = clamp3(x_err * ake + v_err * akd, T(1e4));
     } else if (JM == JM_ALL && js.type == JT_FIXED) {
+        // acos(r_err.w) evaluated as atan2(|r_err.xyz|, r_err.w): same value for a unit quaternion, well
+        // conditioned near the identity (see revolute_angle)
         V3<T> e = qvec(r_err);
         T l = sqrt(dot(e, e));
         T inv = l > T(0) ? T(1) / l : T(0);
-        V3<T> ang_err = e * (inv * safe_acos(r_err.w) * T(2));
+        V3<T> ang_err = e * (inv * atan2(l, r_err.w) * T(2));
         f_out = x_err * ake + v_err * akd;
         t_out = qrot(qA, ang_err) * ake + w_err * (akd * ads);
     }
@@ -421,7 +423,7 @@ PPR_UNROLL
         V3<T> e = qvec(r_err);
         T l = sqrt(dot(e, e));
         T inv = l > T(0) ? T(1) / l : T(0);
-        T ac = safe_acos(r_err.w) * T(2);
+        T ac = atan2(l, r_err.w) * T(2);
         V3<T> nrm = e * inv;
         V3<T> ang_err = nrm * ac;
         f_out = x_err * ake + v_err * akd;
@@ -435,12 +437,14 @@ PPR_UNROLL
         V3<T> g_ang = qrot_inv(qA, g_rot);
         T g_ac = dot(nrm, g_ang);
         V3<T> g_n = g_ang * ac;
+        T den = l * l + r_err.w * r_err.w;
         if (l > T(0)) {
             T ng = dot(nrm, g_n);
-            g_rerr.x += (g_n.x - nrm.x * ng) * inv; g_rerr.y += (g_n.y - nrm.y * ng) * inv;
-            g_rerr.z += (g_n.z - nrm.z * ng) * inv;
+            T g_l = T(2) * g_ac * r_err.w / den;  // d(2 atan2(l, w))/dl
+            g_rerr.x += (g_n.x - nrm.x * ng) * inv + nrm.x * g_l; g_rerr.y += (g_n.y - nrm.y * ng) * inv + nrm.y * g_l;
+            g_rerr.z += (g_n.z - nrm.z * ng) * inv + nrm.z * g_l;
         }
-        g_rerr.w += T(2) * g_ac * safe_acos_adj(r_err.w);
+        if (den > T(0)) g_rerr.w += -T(2) * g_ac * l / den;
         adjC.x += g_armc; adj_xcc -= g_armc;
         if (has_parent) { adj_xcp -= g_armp; }
         V3<T> g_xA = g_armp - g_xerr;

@@ -545,7 +545,6 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     if (M.nc > 0) cm0 = load_mat(M, 0);
     LaneInfo L = lane_setup(M, warp, lane, A.bs);
     // per-env parameters of this body / joint -> shared memory
-    int64_t eb = (int64_t)L.env * M.nb + L.body;
     int64_t ebp = (int64_t)L.env * A.pstride * M.nb + L.body;
     par[0] = A.inv_m[ebp];
 #pragma unroll

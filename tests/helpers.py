@@ -71,3 +71,55 @@ def settle_height(rm, d, penetration=0.003):
     q[:, 1] = q[:, 1] - low - penetration
     d["q_init"] = q.to(d["q_init"].dtype)
     return d
+
+
+def make_mixed_robot():
+    """Synthetic articulation exercising everything the three shipped robots do NOT: FIXED joints, REVOLUTE and
+    COMPOUND joints in one tree, active joint limits, a non-identity joint_X_c rotation on a COMPOUND joint, sphere /
+    capsule contacts (dist > 0), two contact materials with contact damping kd > 0, a non-unit revolute axis and a
+    parent with three children. Drives the GENERIC kernel instance (JM_ALL, LIMITS, QOFF)."""
+    from ppr_diffphys_b200.model import (ArticulationBuilder, RobotModel, JOINT_FREE, JOINT_REVOLUTE, JOINT_COMPOUND,
+                                         JOINT_FIXED, quat_rpy)
+    b = ArticulationBuilder()
+    m1, m2 = (1e4, 0.0, 1e2, 1.0), (5e3, 50.0, 80.0, 0.6)
+    xf = lambda p, rpy: np.concatenate([np.asarray(p, float), quat_rpy(*rpy)])
+    r = b.add_body(-1, JOINT_FREE, armature=0.01, name="root")
+    b.add_shape_box(r, np.zeros(3), quat_rpy(0, 0, 0), 0.2, 0.05, 0.1, 1000.0, m1)
+    a = b.add_body(r, JOINT_REVOLUTE, joint_xform=xf([0.2, -0.05, 0.0], [0.1, 0.2, -0.1]), joint_axis=(0.6, 0.0, 0.8 * 1.5),
+                   lower=-0.1, upper=0.1, limit_ke=50.0, limit_kd=1.0, target_ke=100.0, target_kd=2.0, armature=0.01, name="a")
+    b.add_shape_box(a, np.array([0.0, -0.1, 0.0]), quat_rpy(0, 0, 0), 0.03, 0.1, 0.03, 1000.0, m1)
+    c = b.add_body(a, JOINT_COMPOUND, joint_xform=xf([0.0, -0.2, 0.0], [0.0, 0.1, 0.0]),
+                   joint_xform_child=xf([0, 0, 0], [0.06, -0.04, 0.05]), lower=-0.2, upper=0.2, limit_ke=30.0, limit_kd=0.5,
+                   target_ke=80.0, target_kd=1.0, armature=0.01, name="c")
+    b.add_shape_sphere(c, np.array([0.0, -0.1, 0.0]), quat_rpy(0, 0, 0), 0.05, 1000.0, m2)
+    # identity joint rotation: the product's FIXED-joint angle 2*atan2(|e|, w) equals the reference's literal
+    # 2*acos(w) only for a UNIT relative quaternion; an f32-rounded joint_X_p quaternion (|q|^2 - 1 ~ 1e-7) makes the
+    # literal acos form (not scale invariant, ill-conditioned near identity) drift by (|q|^2 - 1) / angle
+    d = b.add_body(r, JOINT_FIXED, joint_xform=xf([-0.2, 0.0, 0.0], [0.0, 0.0, 0.0]), armature=0.01, name="d")
+    b.add_shape_box(d, np.zeros(3), quat_rpy(0, 0, 0), 0.05, 0.05, 0.05, 1000.0, m1)
+    e = b.add_body(d, JOINT_REVOLUTE, joint_xform=xf([0.0, -0.05, 0.0], [0, 0, 0]), joint_axis=(0.0, 0.0, 1.0),
+                   target_ke=100.0, target_kd=2.0, armature=0.01, name="e")
+    b.add_shape_capsule(e, np.array([0.0, -0.12, 0.0]), quat_rpy(0, 0, np.pi / 2), 0.03, 0.08, 1000.0, m2)
+    f = b.add_body(r, JOINT_COMPOUND, joint_xform=xf([0.0, -0.05, 0.1], [0.2, 0, 0]), target_ke=80.0, target_kd=1.0,
+                   armature=0.01, name="f")
+    b.add_shape_box(f, np.array([0.0, -0.1, 0.0]), quat_rpy(0, 0, 0), 0.03, 0.1, 0.03, 1000.0, m1)
+    b.joint_q[0:7] = [0, 0.4, 0, 0, 0, 0, 1]
+    nb = len(b.body_mass)
+    for i in range(nb):
+        b.body_inertia[i] = b.body_inertia[i] / b.body_mass[i]
+    cb, cp, cd, cm = b.collide()
+    f32 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+    i32 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.int32))
+    ke = [0.0] * 6 + list(b.joint_target_ke[6:])
+    kd = [0.0] * 6 + list(b.joint_target_kd[6:])
+    return RobotModel(name="mixed", joint_type=i32(b.joint_type), joint_parent=i32(b.joint_parent),
+                      joint_X_p=f32(b.joint_X_p), joint_X_c=f32(b.joint_X_c), joint_axis=f32(b.joint_axis),
+                      joint_q_start=i32(b.joint_q_start), joint_qd_start=i32(b.joint_qd_start),
+                      joint_limit_lower=f32(b.joint_limit_lower), joint_limit_upper=f32(b.joint_limit_upper),
+                      joint_limit_ke=f32(b.joint_limit_ke), joint_limit_kd=f32(b.joint_limit_kd),
+                      joint_target_ke=f32(ke), joint_target_kd=f32(kd), body_com=f32(b.body_com),
+                      body_mass=f32(b.body_mass), norm_body_inertia=f32(b.body_inertia), contact_body=i32(cb),
+                      contact_point=f32(cp), contact_dist=f32(cd), contact_material=i32(cm),
+                      shape_materials=f32(b.shape_materials), gravity=f32([0.0, -9.80665, 0.0]),
+                      joint_q_rest=f32(b.joint_q), joint_attach_ke=4000.0, joint_attach_kd=50.0,
+                      body_names=list(b.body_name))

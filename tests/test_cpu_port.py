@@ -63,3 +63,32 @@ def test_cpu_port_fk_adjoint_matches_autograd():
         assert (cbq - bq.detach()).abs().max() < 1e-12 and (cbqd - bqd.detach()).abs().max() < 1e-12
         aq, aqd = cpu.fk_backward(d["q_init"], d["qd_init"], w1, w2)
         assert (aq - gq).abs().max() < 1e-10 and (aqd - gqd).abs().max() < 1e-10
+
+
+def test_generic_feature_set_matches_autograd_oracle():
+    """FIXED + REVOLUTE + COMPOUND in one tree, active limits, non-identity q_off, spheres / capsules, two materials
+    with kd > 0: float64 CPU port (the header the generic CUDA instance compiles) vs the autograd oracle."""
+    from oracle import sim_oracle as so
+    from helpers import make_inputs, make_mixed_robot, settle_height
+    rm = make_mixed_robot()
+    assert rm.nqd == 14 and rm.nq == 15 and len(set(rm.contact_material.tolist())) > 1 and rm.contact_dist.max() > 0
+    stride, F, bs = 8, 3, 4
+    T = stride * (F - 1) + 1
+    rm, d = make_inputs(rm, bs=bs, T=T, seed=17, ang=0.25, res_f_std=0.05, torque_std=0.05, lin_vel=0.3, qd_std=0.05)
+    d = settle_height(rm, d, 0.004)
+    m = so.OracleModel(rm)
+    a = {k: d[k].clone().requires_grad_(True) for k in KEYS}
+    pos, vel, grf, jaf = so.rollout(m, a["q_init"], a["qd_init"], a["torques"], a["res_f"], a["refs"], a["target_ke"],
+                                    a["target_kd"], a["body_inv_mass"], a["body_inertia"], a["body_inv_inertia"], 5e-4,
+                                    stride, F)
+    assert grf.abs().max() > 1.0  # in contact
+    g = torch.Generator().manual_seed(2)
+    wp, wv = torch.randn(pos.shape, generator=g, dtype=torch.float64), torch.randn(vel.shape, generator=g,
+                                                                                    dtype=torch.float64) * 0.1
+    grads = torch.autograd.grad((pos * wp).sum() + (vel * wv).sum(), [a[k] for k in KEYS])
+    cpu = CpuRollout(rm)
+    p2, v2, g2, j2 = cpu.forward(d, 5e-4, stride, F, want_forces=True)
+    assert (p2 - pos.detach()).abs().max() < 1e-11 and (g2 - grf).abs().max() < 1e-6 and (j2 - jaf).abs().max() < 1e-6
+    out = cpu.backward(wp, wv)
+    for k, gr in zip(KEYS, grads):
+        assert (out[k] - gr).norm() <= 1e-9 * gr.norm() + 1e-12, k

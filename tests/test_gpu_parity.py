@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import make_inputs, settle_height
+from helpers import make_inputs, make_mixed_robot, settle_height
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -126,6 +126,43 @@ def test_live_oracle_parity_null_forces(robot, bs):
     grads = torch.autograd.grad(loss_o, [o[k] for k in keys])
     for k, g in zip(keys, grads):
         assert rel(a[k].grad, g) <= (GRAD_RTOL_STIFF if robot == "laikago" else GRAD_RTOL), k
+
+
+def test_generic_kernel_instance_mixed_features():
+    """The generic instance (JM_ALL, LIMITS, QOFF): FIXED + REVOLUTE + COMPOUND joints, active limit springs,
+    non-identity joint_X_c, sphere / capsule contacts with thickness, two materials with kd > 0, torques and res_f."""
+    from oracle import sim_oracle as so
+    from ppr_diffphys_b200 import SimEnv
+    rm = make_mixed_robot()
+    stride, F, bs = 16, 3, 5
+    T = stride * (F - 1) + 1
+    rm, d = make_inputs(rm, bs=bs, T=T, seed=17, ang=0.25, res_f_std=0.05, torque_std=0.05, lin_vel=0.3, qd_std=0.05)
+    d = settle_height(rm, d, 0.004)
+    d = {k: v.float().double() for k, v in d.items()}
+    dev = torch.device("cuda:0")
+    env = SimEnv(rm)
+    a, _, _ = flat_args(d, dev)
+    pos, vel, caller = run_cuda(env, a, bs, T, stride)
+    m = so.OracleModel(rm)
+    o = {k: d[k].clone().requires_grad_(True) for k in KEYS}
+    opos, ovel, ogrf, ojaf = so.rollout(m, o["q_init"], o["qd_init"], o["torques"], o["res_f"], o["refs"],
+                                        o["target_ke"], o["target_kd"], o["body_inv_mass"], o["body_inertia"],
+                                        o["body_inv_inertia"], 5e-4, stride, F)
+    assert ogrf.abs().max() > 1.0
+    assert (pos.cpu().double() - opos.detach().reshape(F, -1, 7)).abs().max() <= POS_TOL
+    assert rel(torch.stack(caller.grfs), ogrf) <= 1e-3 and rel(torch.stack(caller.jafs), ojaf) <= 1e-3
+    g = torch.Generator().manual_seed(2)
+    wp = torch.randn(opos.shape, generator=g, dtype=torch.float64)
+    wv = torch.randn(ovel.shape, generator=g, dtype=torch.float64) * 0.1
+    torch.autograd.backward([pos, vel], [wp.reshape(F, -1, 7).to(dev, torch.float32),
+                                         wv.reshape(F, -1, 6).to(dev, torch.float32)])
+    grads = torch.autograd.grad((opos * wp).sum() + (ovel * wv).sum(), [o[k] for k in KEYS])
+    for k, gr in zip(KEYS, grads):
+        assert rel(a[k].grad, gr) <= GRAD_RTOL, (k, rel(a[k].grad, gr))
+    # FK of the generic instance
+    bq, bqd = env.fk(a["q_init"].detach().view(bs, -1), a["qd_init"].detach().view(bs, -1))
+    obq, obqd = so.eval_fk(m, d["q_init"], d["qd_init"])
+    assert (bq.cpu().double() - obq).abs().max() < 2e-6 and (bqd.cpu().double() - obqd).abs().max() < 2e-5
 
 
 @pytest.mark.parametrize("robot", ["laikago", "human", "quad"])
