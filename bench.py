@@ -191,6 +191,7 @@ def run_gpu_arm(args):
     caller = Caller(env, bs, nsteps, stride)
     host = make_batch(env, bs, nsteps, seed=rank, clearance=w["clearance"], lin_vel=w["lin_vel"], pinned_host=True)
     nI = torch.as_tensor(rm.norm_body_inertia, device=dev)
+    nI_inv = torch.linalg.inv(nI)
     # shared parameters (what the reference optimises): PD gains + body mass; per-env replication like dp_model.py:723-725
     p_ke = torch.as_tensor(rm.joint_target_ke, device=dev).clone().requires_grad_(True)
     p_kd = torch.as_tensor(rm.joint_target_kd, device=dev).clone().requires_grad_(True)
@@ -207,7 +208,7 @@ def run_gpu_arm(args):
         else:                       # un-replicated parameters: the kernels read one shared copy
             ke, kd, mass = p_ke, p_kd, p_mass
             inv_m, I = 1.0 / p_mass, nI * p_mass[:, None, None]
-            inv_I = torch.linalg.inv(I)
+            inv_I = nI_inv * inv_m[:, None, None]       # inverse(nI * m) = inverse(nI) / m
         pos, vel = ForwardWarp.apply(q_init, qd_init, None, None, refs, ke, kd, mass, inv_m, I, inv_I, caller)
         loss = (pos[-1, :, :3] - pos[0, :, :3]).pow(2).mean() + 1e-3 * vel[-1].pow(2).mean()
         for p in (p_ke, p_kd, p_mass):

@@ -85,12 +85,21 @@ __device__ __forceinline__ WrenchF shf_wrench(const WrenchF& w, int src) {
 // Ampere-style asynchronous global->shared copies (LDGSTS): the adjoint kernel streams the NEXT checkpoint row into
 // shared memory while it differentiates the current substep, so the ~700-cycle DRAM latency is never on the
 // critical path and no registers are held for the prefetched values.
-__device__ __forceinline__ void cp_async4(volatile float* smem_dst, const float* gsrc) {
+// 16-byte .cg copies: bypass L1 so that the streamed checkpoint does not evict the contact-point table from it.
+__device__ __forceinline__ void cp_async16(volatile float* smem_dst, const float* gsrc) {
     unsigned sa = (unsigned)__cvta_generic_to_shared((const void*)smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+// one checkpoint row of a warp = PPR_CKPT_FLOATS x 32 floats, contiguous in HBM: 6 x 16 B per lane
+__device__ __forceinline__ void cp_async_row(volatile float* smem_row, const float* grow, int lane) {
+#pragma unroll
+    for (int i = 0; i < PPR_CKPT_FLOATS * 32 / 4 / 32; ++i) cp_async16(smem_row + (i * 32 + lane) * 4, grow + (i * 32 + lane) * 4);
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// remove_nan of the reference (dp_utils.py:43-57, clip = False) applied at the store: NaN -> 0, everything else
+// (including +-inf) untouched. Saves one full pass over every gradient tensor on the host side.
+__device__ __forceinline__ float nan0(float v) { return v != v ? 0.f : v; }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -424,9 +433,9 @@ __device__ __forceinline__ void warp_fk_adjoint(const DevModel& M, const LaneInf
     if (L.valid) {
         int ncoord = L.type == JT_FREE ? 7 : L.ndof;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) if (k < ncoord) adj_q[(int64_t)L.env * M.nq + L.qs + k] = ajq[k];
+        for (int k = 0; k < 7; ++k) if (k < ncoord) adj_q[(int64_t)L.env * M.nq + L.qs + k] = nan0(ajq[k]);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) if (k < L.ndof) adj_qd[(int64_t)L.env * M.nqd + L.qds + k] = ajqd[k];
+        for (int k = 0; k < 6; ++k) if (k < L.ndof) adj_qd[(int64_t)L.env * M.nqd + L.qds + k] = nan0(ajqd[k]);
     }
 }
 
@@ -619,14 +628,15 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     __shared__ float sm_st[PPR_NSTATIC * 32];  // per BLOCK: every warp stages the same per-body values
     __shared__ float sm_par[PPR_NPAR * PPR_BLOCK];
     __shared__ float sm_acc[18 * PPR_BLOCK];
-    __shared__ float sm_row[PPR_CKPT_FLOATS * PPR_BLOCK];  // the prefetched checkpoint row, [c][thread]
+    __shared__ __align__(16) float sm_row[PPR_WARPS * PPR_CKPT_FLOATS * 32];  // prefetched checkpoint rows, [warp][c][lane]
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     int* clist = clist_all + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
     volatile float* st = sm_st;
     volatile float* par = sm_par + threadIdx.x;
     volatile float* acc = sm_acc + threadIdx.x;
-    volatile float* row = sm_row + threadIdx.x;
+    volatile float* roww = sm_row + (threadIdx.x >> 5) * PPR_CKPT_FLOATS * 32;  // this warp's row buffer
+    volatile float* row = roww + (threadIdx.x & 31);
     if (warp >= A.nwarps) return;
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
     if (M.nc > 0) cm0 = load_mat(M, 0);
@@ -656,7 +666,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
 
     float a_inv_m = 0.f, a_ke[3] = {0, 0, 0}, a_kd[3] = {0, 0, 0};
 
-    const float* ck = A.ckpt + (warp * PPR_CKPT_FLOATS) * 32 + lane;
+    const float* ckw = A.ckpt + (warp * PPR_CKPT_FLOATS) * 32;  // this warp's rows (3 kB each, 16-byte aligned)
     const int64_t ck_step = A.nwarps * PPR_CKPT_FLOATS * 32;
     const int64_t last = A.nsteps - 1;
 
@@ -688,30 +698,26 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         if (t == 0) break;
         int64_t tp = t - 1;  // differentiate substep tp -> t
         if (t == last) {     // first row: nothing was prefetched yet
-            const float* c0 = ck + tp * ck_step;
-#pragma unroll
-            for (int i = 0; i < PPR_CKPT_FLOATS; ++i) cp_async4(row + i * PPR_BLOCK, c0 + i * 32);
+            cp_async_row(roww, ckw + tp * ck_step, lane);
             cp_async_commit();
         }
         cp_async_wait_all();
+        __syncwarp();        // a lane's 19+5 values were fetched by other lanes
         BodyF s;
         WrenchF F;
-        s.x = v3<float>(row[0 * PPR_BLOCK], row[1 * PPR_BLOCK], row[2 * PPR_BLOCK]);
-        s.r = q4<float>(row[3 * PPR_BLOCK], row[4 * PPR_BLOCK], row[5 * PPR_BLOCK], row[6 * PPR_BLOCK]);
-        s.w = v3<float>(row[7 * PPR_BLOCK], row[8 * PPR_BLOCK], row[9 * PPR_BLOCK]);
-        s.v = v3<float>(row[10 * PPR_BLOCK], row[11 * PPR_BLOCK], row[12 * PPR_BLOCK]);
-        F.t = v3<float>(row[13 * PPR_BLOCK], row[14 * PPR_BLOCK], row[15 * PPR_BLOCK]);
-        F.f = v3<float>(row[16 * PPR_BLOCK], row[17 * PPR_BLOCK], row[18 * PPR_BLOCK]);
+        s.x = v3<float>(row[0 * 32], row[1 * 32], row[2 * 32]);
+        s.r = q4<float>(row[3 * 32], row[4 * 32], row[5 * 32], row[6 * 32]);
+        s.w = v3<float>(row[7 * 32], row[8 * 32], row[9 * 32]);
+        s.v = v3<float>(row[10 * 32], row[11 * 32], row[12 * 32]);
+        F.t = v3<float>(row[13 * 32], row[14 * 32], row[15 * 32]);
+        F.f = v3<float>(row[16 * 32], row[17 * 32], row[18 * 32]);
         ContactRec rec;
-        rec.cnt = __float_as_uint(row[19 * PPR_BLOCK]);
-        rec.lo = (unsigned long long)__float_as_uint(row[20 * PPR_BLOCK]) |
-                 ((unsigned long long)__float_as_uint(row[21 * PPR_BLOCK]) << 32);
-        rec.hi = (unsigned long long)__float_as_uint(row[22 * PPR_BLOCK]) |
-                 ((unsigned long long)__float_as_uint(row[23 * PPR_BLOCK]) << 32);
-        if (tp > 0) {  // every slot is private to its thread: safe to refill as soon as it has been read
-            const float* cn = ck + (tp - 1) * ck_step;
-#pragma unroll
-            for (int i = 0; i < PPR_CKPT_FLOATS; ++i) cp_async4(row + i * PPR_BLOCK, cn + i * 32);
+        rec.cnt = __float_as_uint(row[19 * 32]);
+        rec.lo = (unsigned long long)__float_as_uint(row[20 * 32]) | ((unsigned long long)__float_as_uint(row[21 * 32]) << 32);
+        rec.hi = (unsigned long long)__float_as_uint(row[22 * 32]) | ((unsigned long long)__float_as_uint(row[23 * 32]) << 32);
+        __syncwarp();        // everyone has read the row: refill it with the next (earlier) one
+        if (tp > 0) {
+            cp_async_row(roww, ckw + (tp - 1) * ck_step, lane);
             cp_async_commit();
         }
         const F3 com = st_vec3(st, ST_COM, L.body);
@@ -756,8 +762,8 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
             int64_t row = (tp * A.bs + L.env) * M.nqd + L.qds;
 #pragma unroll
             for (int k = 0; k < 3; ++k) if (jon && k < L.ndof) {
-                A.adj_refs[row + k] = g_target[k];
-                if (A.adj_torques) A.adj_torques[row + k] = g_act[k];
+                A.adj_refs[row + k] = nan0(g_target[k]);
+                if (A.adj_torques) A.adj_torques[row + k] = nan0(g_act[k]);
             }
             if (!jon) for (int k = 0; k < L.ndof; ++k) {
                 A.adj_refs[row + k] = 0.f;
@@ -767,7 +773,11 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         // K3^T
         warp_contacts_adj(M, L, lane, s, xc, cm0, st, clist, rec, adjF, adjS, adj_xc);
         // K2^T
-        if (A.adj_res_f && L.valid) store_wrench_row(A.adj_res_f + ((tp * A.bs + L.env) * M.nb + L.body) * 6, adjF);
+        if (A.adj_res_f && L.valid) {
+            float* r = A.adj_res_f + ((tp * A.bs + L.env) * M.nb + L.body) * 6;
+            r[0] = nan0(adjF.t.x); r[1] = nan0(adjF.t.y); r[2] = nan0(adjF.t.z);
+            r[3] = nan0(adjF.f.x); r[4] = nan0(adjF.f.y); r[5] = nan0(adjF.f.z);
+        }
         // world COM -> pose
         adjS.x += adj_xc;
         adjS.r += qrot_adj_q(s.r, com, adj_xc);
@@ -782,12 +792,12 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         warp_fk_adjoint<JM>(M, L2, s0, adjN, jq, jqd, A.adj_q_init, A.adj_qd_init);
     }
     if (L.valid) {
-        A.adj_inv_m[eb] = a_inv_m;
+        A.adj_inv_m[eb] = nan0(a_inv_m);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) { A.adj_I[eb * 9 + i] = acc[i * PPR_BLOCK]; A.adj_inv_I[eb * 9 + i] = acc[(9 + i) * PPR_BLOCK]; }
+        for (int i = 0; i < 9; ++i) { A.adj_I[eb * 9 + i] = nan0(acc[i * PPR_BLOCK]); A.adj_inv_I[eb * 9 + i] = nan0(acc[(9 + i) * PPR_BLOCK]); }
         int64_t d = (int64_t)L.env * M.nqd + L.qds;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) if (jon && k < L.ndof) { A.adj_ke[d + k] = a_ke[k]; A.adj_kd[d + k] = a_kd[k]; }
+        for (int k = 0; k < 3; ++k) if (jon && k < L.ndof) { A.adj_ke[d + k] = nan0(a_ke[k]); A.adj_kd[d + k] = nan0(a_kd[k]); }
         if (!jon) for (int k = 0; k < L.ndof; ++k) { A.adj_ke[d + k] = 0.f; A.adj_kd[d + k] = 0.f; }
     }
 }

@@ -150,6 +150,7 @@ class ImitationModel(nn.Module):
         self.target_kd = nn.Parameter(torch.as_tensor(rm.joint_target_kd))
         self.body_mass = nn.Parameter(torch.as_tensor(rm.body_mass))
         self.register_buffer("norm_body_inertia", torch.as_tensor(rm.norm_body_inertia))
+        self.register_buffer("norm_body_inertia_inv", torch.linalg.inv(torch.as_tensor(rm.norm_body_inertia)))
         N = self.total_frames
         self.root_pose_mlp = TimeMLP(N, 6, time_scale=0.1, output_scale=0.5)
         self.joint_angle_mlp = TimeMLP(N, self.n_dof)
@@ -263,9 +264,9 @@ class ImitationModel(nn.Module):
         qd_init = convert_ppr_warp(queried_qd[0].view(bs, -1)).reshape(-1)
         inv_m = 1.0 / self.body_mass
         I = self.norm_body_inertia * self.body_mass[:, None, None]
+        inv_I = self.norm_body_inertia_inv * inv_m[:, None, None]   # inverse(nI * m) = inverse(nI) / m
         sim_position, sim_velocity = ForwardWarp.apply(q_init, qd_init, None, None, ref_ja, self.target_ke,
-                                                       self.target_kd, self.body_mass, inv_m, I, torch.linalg.inv(I),
-                                                       self)
+                                                       self.target_kd, self.body_mass, inv_m, I, inv_I, self)
         sim_velocity = convert_ppr_warp(sim_velocity)
         f2s = self.frame2step
         qq = queried_q[f2s].reshape(F, bs, -1)

@@ -193,8 +193,9 @@ class SimEnv:
 
 
 def _scrub(g):
-    """remove_nan (dp_utils.py:43-57, clip=False): NaN -> 0."""
-    return None if g is None else torch.nan_to_num(g, nan=0.0, posinf=float("inf"), neginf=float("-inf"))
+    """remove_nan (dp_utils.py:43-57, clip=False): NaN -> 0. The rollout adjoint kernel already applies it at every
+    gradient store (`nan0` in ppr_kernels.cu), so this is the identity for its outputs."""
+    return g
 
 
 class ForwardKinematics(torch.autograd.Function):
@@ -229,9 +230,10 @@ class ForwardKinematics(torch.autograd.Function):
         aq = _f32c(z(adj_body_q, 7), env.device).permute(1, 0, 2, 3).contiguous().view(T * bs, env.nb, 7)
         aqd = _f32c(z(adj_body_qd, 6), env.device).permute(1, 0, 2, 3).contiguous().view(T * bs, env.nb, 6)
         gq, gqd = env.fk_backward(q, qd, aq, aqd)
-        # reference post-processing (dp_model.py:1109-1110,1122-1123): NaN -> 0, upper clamp at +1 only
-        gq = torch.nan_to_num(gq, nan=0.0).clamp(max=1.0).view(T, bs, nq)
-        gqd = torch.nan_to_num(gqd, nan=0.0).clamp(max=1.0).view(T, bs, nq - 1)
+        # reference post-processing (dp_model.py:1109-1110,1122-1123): NaN -> 0 (done by the kernel at the store),
+        # upper clamp at +1 only
+        gq = gq.clamp_(max=1.0).view(T, bs, nq)
+        gqd = gqd.clamp_(max=1.0).view(T, bs, nq - 1)
         if not ctx.is_cuda:
             gq, gqd = gq.cpu(), gqd.cpu()
         return (gq if ctx.needs_input_grad[0] else None, gqd if ctx.needs_input_grad[1] else None, None)
