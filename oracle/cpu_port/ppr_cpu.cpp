@@ -122,8 +122,8 @@ void fk_env_adj(const CpuModel<T>& m, const T* jq, const T* jqd, const Body<T>* 
 
 // forces of one substep for one env; returns F (total), optionally grf / jaf
 template <class T>
-void forces_env(const CpuModel<T>& m, const Body<T>* s, const V3<T>* xc, const T* res_f, const T* refs, const T* act,
-                const T* ke, const T* kd, Wrench<T>* F, T* grf, T* jaf) {
+void forces_env(const CpuModel<T>& m, const Body<T>* s, const M3<T>* R, const V3<T>* xc, const T* res_f, const T* refs,
+                const T* act, const T* ke, const T* kd, Wrench<T>* F, T* grf, T* jaf) {
     for (int b = 0; b < m.nb; ++b) {
         if (res_f) { F[b].t = v3<T>(res_f[6 * b], res_f[6 * b + 1], res_f[6 * b + 2]);
                      F[b].f = v3<T>(res_f[6 * b + 3], res_f[6 * b + 4], res_f[6 * b + 5]); }
@@ -131,7 +131,7 @@ void forces_env(const CpuModel<T>& m, const Body<T>* s, const V3<T>* xc, const T
     }
     for (int k = 0; k < m.nc; ++k) {
         int b = m.cbody[k];
-        contact_point_fwd(s[b], xc[b], m.cpoint[k], m.cdist[k], m.cmat[k], F[b]);
+        contact_point_fwd(s[b], R[b], xc[b], m.cpoint[k], m.cdist[k], m.cmat[k], F[b]);
     }
     if (grf) for (int b = 0; b < m.nb; ++b) store_wrench(F[b], grf + 6 * b);
     for (int j = 0; j < m.nb; ++j) {
@@ -139,7 +139,7 @@ void forces_env(const CpuModel<T>& m, const Body<T>* s, const V3<T>* xc, const T
         JointCtl<T> c = load_ctl(m, j, refs, act, ke, kd);
         V3<T> t, f, ap, ac;
         Body<T> P = p >= 0 ? s[p] : body_identity<T>();
-        joint_fwd(m.js[j], c, m.ake, m.akd, P, p >= 0 ? xc[p] : vzero<T>(), p >= 0, s[j], xc[j], t, f, ap, ac);
+        joint_fwd(m.js[j], c, m.ake, m.akd, P, p >= 0 ? xc[p] : vzero<T>(), p >= 0, s[j], R[j], xc[j], t, f, ap, ac);
         if (m.type[j] == JT_FREE) continue;
         if (p >= 0) { F[p].t += t + cross(ap, f); F[p].f += f; }
         F[j].t -= t + cross(ac, f); F[j].f -= f;
@@ -161,6 +161,7 @@ int rollout_forward(const ppr_model_desc* d, int64_t bs, int64_t T_, int64_t str
     for (int64_t e = 0; e < bs; ++e) {
         std::vector<Body<T>> s(nb), s1(nb);
         std::vector<V3<T>> xc(nb);
+        std::vector<M3<T>> R(nb);
         std::vector<Wrench<T>> F(nb);
         fk_env(m, q_init + e * nq, qd_init + e * nqd, s.data());
         for (int64_t t = 0; t < T_; ++t) {
@@ -170,13 +171,13 @@ int rollout_forward(const ppr_model_desc* d, int64_t bs, int64_t T_, int64_t str
             int64_t fidx = t / stride;
             if (frame) for (int b = 0; b < nb; ++b)
                 store_body(s[b], out_pos + ((fidx * bs + e) * nb + b) * 7, out_vel + ((fidx * bs + e) * nb + b) * 6);
-            for (int b = 0; b < nb; ++b) xc[b] = s[b].x + qrot(s[b].r, m.com[b]);
-            forces_env(m, s.data(), xc.data(), res_f ? res_f + (t * bs + e) * nb * 6 : nullptr,
+            for (int b = 0; b < nb; ++b) { R[b] = qmat(s[b].r); xc[b] = s[b].x + mrot(R[b], m.com[b]); }
+            forces_env(m, s.data(), R.data(), xc.data(), res_f ? res_f + (t * bs + e) * nb * 6 : nullptr,
                        refs + (t * bs + e) * nqd, torques ? torques + (t * bs + e) * nqd : nullptr, ke + e * nqd,
                        kd + e * nqd, F.data(), (frame && out_grf) ? out_grf + (fidx * bs + e) * nb * 6 : nullptr,
                        (frame && out_jaf) ? out_jaf + (fidx * bs + e) * nb * 6 : nullptr);
             for (int b = 0; b < nb; ++b)
-                s1[b] = integrate_fwd(s[b], xc[b], m.com[b], F[b], inv_m[e * nb + b], I + (e * nb + b) * 9,
+                s1[b] = integrate_fwd(s[b], R[b], xc[b], m.com[b], F[b], inv_m[e * nb + b], I + (e * nb + b) * 9,
                                       inv_I + (e * nb + b) * 9, m.g, dt);
             s.swap(s1);
         }
@@ -195,6 +196,7 @@ int rollout_backward(const ppr_model_desc* d, int64_t bs, int64_t T_, int64_t st
 #pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < bs; ++e) {
         std::vector<Body<T>> s(nb), adjS(nb), adjN(nb);
+        std::vector<M3<T>> R(nb), G(nb);
         std::vector<V3<T>> xc(nb), adj_xc(nb);
         std::vector<Wrench<T>> F(nb), adjF(nb);
         for (int k = 0; k < nqd; ++k) { adj_ke[e * nqd + k] = 0; adj_kd[e * nqd + k] = 0; }
@@ -224,16 +226,16 @@ int rollout_backward(const ppr_model_desc* d, int64_t bs, int64_t T_, int64_t st
         for (int64_t t = last - 1; t >= 0; --t) {
             const T* st = states + ((t * bs + e) * nb) * 13;
             for (int b = 0; b < nb; ++b) s[b] = load_body(st + 13 * b, st + 13 * b + 7);
-            for (int b = 0; b < nb; ++b) xc[b] = s[b].x + qrot(s[b].r, m.com[b]);
+            for (int b = 0; b < nb; ++b) { R[b] = qmat(s[b].r); xc[b] = s[b].x + mrot(R[b], m.com[b]); }
             const T* refs_t = refs + (t * bs + e) * nqd;
             const T* act_t = torques ? torques + (t * bs + e) * nqd : nullptr;
-            forces_env(m, s.data(), xc.data(), res_f ? res_f + (t * bs + e) * nb * 6 : nullptr, refs_t, act_t,
+            forces_env(m, s.data(), R.data(), xc.data(), res_f ? res_f + (t * bs + e) * nb * 6 : nullptr, refs_t, act_t,
                        ke + e * nqd, kd + e * nqd, F.data(), (T*)nullptr, (T*)nullptr);
             // K5^T
             for (int b = 0; b < nb; ++b) {
-                adjS[b] = body_zero<T>(); adj_xc[b] = vzero<T>();
-                integrate_adj(s[b], xc[b], m.com[b], F[b], inv_m[e * nb + b], I + (e * nb + b) * 9,
-                              inv_I + (e * nb + b) * 9, m.g, dt, adjN[b], adjS[b], adj_xc[b], adjF[b],
+                adjS[b] = body_zero<T>(); adj_xc[b] = vzero<T>(); G[b] = m3_zero<T>();
+                integrate_adj(s[b], R[b], xc[b], m.com[b], F[b], inv_m[e * nb + b], I + (e * nb + b) * 9,
+                              inv_I + (e * nb + b) * 9, m.g, dt, adjN[b], adjS[b], G[b], adj_xc[b], adjF[b],
                               adj_inv_m[e * nb + b], adj_I + (e * nb + b) * 9, adj_inv_I + (e * nb + b) * 9);
             }
             // K4^T
@@ -250,8 +252,8 @@ int rollout_backward(const ppr_model_desc* d, int64_t bs, int64_t T_, int64_t st
                 Body<T> adjP = body_zero<T>();
                 V3<T> adj_xcp = vzero<T>();
                 Wrench<T> aFp = p >= 0 ? adjF[p] : wrench_zero<T>();
-                joint_adj(m.js[j], c, m.ake, m.akd, P, p >= 0 ? xc[p] : vzero<T>(), p >= 0, s[j], xc[j], aFp, adjF[j],
-                          adjP, adj_xcp, adjS[j], adj_xc[j], a_target, a_act, a_ke, a_kd);
+                joint_adj(m.js[j], c, m.ake, m.akd, P, p >= 0 ? xc[p] : vzero<T>(), p >= 0, s[j], R[j], xc[j], aFp,
+                          adjF[j], adjP, adj_xcp, adjS[j], G[j], adj_xc[j], a_target, a_act, a_ke, a_kd);
                 if (p >= 0) { body_acc(adjS[p], adjP); adj_xc[p] += adj_xcp; }
                 for (int k = 0; k < m.ndof[j] && k < 3; ++k) {
                     int dd = m.qds[j] + k;
@@ -264,14 +266,15 @@ int rollout_backward(const ppr_model_desc* d, int64_t bs, int64_t T_, int64_t st
             // K3^T
             for (int k = 0; k < m.nc; ++k) {
                 int b = m.cbody[k];
-                contact_point_adj(s[b], xc[b], m.cpoint[k], m.cdist[k], m.cmat[k], adjF[b], adjS[b], adj_xc[b]);
+                contact_point_adj(s[b], R[b], xc[b], m.cpoint[k], m.cdist[k], m.cmat[k], adjF[b], adjS[b], G[b], adj_xc[b]);
             }
             // K2^T
             if (adj_res_f) for (int b = 0; b < nb; ++b) store_wrench(adjF[b], adj_res_f + ((t * bs + e) * nb + b) * 6);
             // world-COM adjoint -> (x, r)
             for (int b = 0; b < nb; ++b) {
                 adjS[b].x += adj_xc[b];
-                adjS[b].r += qrot_adj_q(s[b].r, m.com[b], adj_xc[b]);
+                m3_acc(G[b], adj_xc[b], m.com[b]);
+                adjS[b].r += qmat_adj(s[b].r, G[b]);
             }
             add_seed(t, adjS);
             adjN.swap(adjS);

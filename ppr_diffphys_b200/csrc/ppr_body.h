@@ -9,6 +9,10 @@
 // intermediates from the saved body state; nothing but (body_q, body_qd) is ever stored per substep.
 //
 // Conventions: transform (p, q xyzw); twist / wrench (angular, linear); ground plane y = 0, normal +Y.
+//
+// Rotations by a body's OWN quaternion go through its rotation matrix Rb = qmat(b.r) (built once per substep by the
+// caller) and, in the adjoint functions, their d/d(b.r) is accumulated as G += (rank-1) with G = dL/dRb; the caller
+// converts once per body and substep with qmat_adj(b.r, G) (ppr_math.h).
 #pragma once
 #include "ppr_math.h"
 
@@ -59,8 +63,9 @@ template <int JM> PPR_HD bool jm_has(int type) {
 // ------------------------------------------------------------------------------------------ contacts (K3)
 // Subtracts the ground-contact wrench of one contact point from F. xc = world COM of the body.
 template <class T>
-PPR_HD bool contact_point_fwd(const Body<T>& b, V3<T> xc, V3<T> p, T dist, ContactMat<T> m, Wrench<T>& F) {
-    V3<T> cp = b.x + qrot(b.r, p);
+PPR_HD bool contact_point_fwd(const Body<T>& b, const M3<T>& Rb, V3<T> xc, V3<T> p, T dist, ContactMat<T> m,
+                              Wrench<T>& F) {
+    V3<T> cp = b.x + mrot(Rb, p);
     cp.y -= dist;
     T c = cp.y;
     if (c > T(0)) return false;
@@ -82,9 +87,9 @@ PPR_HD bool contact_point_fwd(const Body<T>& b, V3<T> xc, V3<T> p, T dist, Conta
 
 // Reverse of the above: adjF = adjoint of the body's wrench; accumulates into adjB (x, r, w, v) and adj_xc.
 template <class T>
-PPR_HD void contact_point_adj(const Body<T>& b, V3<T> xc, V3<T> p, T dist, ContactMat<T> m, const Wrench<T>& adjF,
-                              Body<T>& adjB, V3<T>& adj_xc) {
-    V3<T> cp = b.x + qrot(b.r, p);
+PPR_HD void contact_point_adj(const Body<T>& b, const M3<T>& Rb, V3<T> xc, V3<T> p, T dist, ContactMat<T> m,
+                              const Wrench<T>& adjF, Body<T>& adjB, M3<T>& G, V3<T>& adj_xc) {
+    V3<T> cp = b.x + mrot(Rb, p);
     cp.y -= dist;
     T c = cp.y;
     if (c > T(0)) return;
@@ -130,7 +135,7 @@ PPR_HD void contact_point_adj(const Body<T>& b, V3<T> xc, V3<T> p, T dist, Conta
     g_cp.y += g_c;
     adj_xc -= g_rr;
     adjB.x += g_cp;
-    adjB.r += qrot_adj_q(b.r, p, g_cp);
+    m3_acc(G, g_cp, p);
 }
 
 // ------------------------------------------------------------------------------------------ joints (K4)
@@ -238,8 +243,8 @@ template <class T> PPR_HD Q4<T> compound_decompose_adj(Q4<T> q_pc, const Compoun
 //   F_parent += (t + arm_p x f, f),  F_child -= (t + arm_c x f, f)      (integrator_euler.py:448-451)
 template <class T, int JM = JM_ALL, bool LIMITS = true, bool QOFF = true>
 PPR_HD void joint_fwd(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T akd, const Body<T>& P, V3<T> xcp,
-                      bool has_parent, const Body<T>& C, V3<T> xcc, V3<T>& t_out, V3<T>& f_out, V3<T>& arm_p,
-                      V3<T>& arm_c) {
+                      bool has_parent, const Body<T>& C, const M3<T>& Rc, V3<T> xcc, V3<T>& t_out, V3<T>& f_out,
+                      V3<T>& arm_p, V3<T>& arm_c) {
     t_out = vzero<T>(); f_out = vzero<T>();
     V3<T> xA = P.x + qrot(P.r, js.xpj);
     Q4<T> qA = qmul(P.r, js.qpj);
@@ -251,7 +256,7 @@ PPR_HD void joint_fwd(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
     V3<T> v_err = C.v - P.v, w_err = C.w - P.w;
     const T ads = T(0.01);
     if (JM != JM_COMPOUND && js.type == JT_REVOLUTE) {
-        V3<T> axis_p = qrot(qA, js.axis), axis_c = qrot(C.r, js.axis);
+        V3<T> axis_p = qrot(qA, js.axis), axis_c = mrot(Rc, js.axis);
         T q = revolute_angle(js.axis, r_err);
         T qd = dot(w_err, axis_p);
         T sc = c.ke[0] * (q - c.target[0]) + c.kd[0] * qd + c.act[0] -
@@ -264,10 +269,11 @@ PPR_HD void joint_fwd(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
         const T* ang = dec.ang;
         Q4<T> qw = QOFF ? qmul(qA, js.qoff) : qA;
         V3<T> ax[3] = {v3<T>(T(1), T(0), T(0)), dec.e1, dec.e2};
+        const M3<T> Mw = qmat(qw);
         V3<T> t = vzero<T>();
 PPR_UNROLL
         for (int k = 0; k < 3; ++k) {
-            V3<T> aw = qrot(qw, ax[k]);
+            V3<T> aw = mrot(Mw, ax[k]);
             T qd = dot(aw, w_err);
             T sc = c.ke[k] * (ang[k] - c.target[k]) + c.kd[k] * qd + c.act[k] -
                    (LIMITS ? joint_limit_force(ang[k], qd, c.lo[k], c.hi[k], c.lke[k], c.lkd[k]) : T(0));
@@ -291,9 +297,9 @@ PPR_UNROLL
 // Accumulates into adjP / adj_xcp (parent state, parent world-COM), adjC / adj_xcc and the per-dof parameter adjoints.
 template <class T, int JM = JM_ALL, bool LIMITS = true, bool QOFF = true>
 PPR_HD void joint_adj(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T akd, const Body<T>& P, V3<T> xcp,
-                      bool has_parent, const Body<T>& C, V3<T> xcc, const Wrench<T>& adjFp, const Wrench<T>& adjFc,
-                      Body<T>& adjP, V3<T>& adj_xcp, Body<T>& adjC, V3<T>& adj_xcc, T* adj_target, T* adj_act,
-                      T* adj_ke, T* adj_kd) {
+                      bool has_parent, const Body<T>& C, const M3<T>& Rc, V3<T> xcc, const Wrench<T>& adjFp,
+                      const Wrench<T>& adjFc, Body<T>& adjP, V3<T>& adj_xcp, Body<T>& adjC, M3<T>& Gc, V3<T>& adj_xcc,
+                      T* adj_target, T* adj_act, T* adj_ke, T* adj_kd) {
     if (js.type == JT_FREE) return;
     // ---- recompute forward
     V3<T> xA = P.x + qrot(P.r, js.xpj);
@@ -317,7 +323,7 @@ PPR_HD void joint_adj(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
     // forward values of t, f are needed for the arm adjoints and clamp masks -> computed per type below
 
     if (JM != JM_COMPOUND && js.type == JT_REVOLUTE) {
-        V3<T> axis_p = qrot(qA, js.axis), axis_c = qrot(C.r, js.axis);
+        V3<T> axis_p = qrot(qA, js.axis), axis_c = mrot(Rc, js.axis);
         T q = revolute_angle(js.axis, r_err);
         T qd = dot(w_err, axis_p);
         T sc = c.ke[0] * (q - c.target[0]) + c.kd[0] * qd + c.act[0] -
@@ -339,7 +345,7 @@ PPR_HD void joint_adj(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
         g_axp += w_err * g_qd;
         revolute_angle_adj(js.axis, r_err, g_q, g_rerr);
         g_qA += qrot_adj_q(qA, js.axis, g_axp);
-        g_Cr += qrot_adj_q(C.r, js.axis, g_axc);
+        m3_acc(Gc, g_axc, js.axis);
         // arms
         adjC.x += g_armc; adj_xcc -= g_armc;
         if (has_parent) { adj_xcp -= g_armp; }
@@ -366,9 +372,10 @@ PPR_HD void joint_adj(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
         V3<T> aw[3];
         T qd[3], sc[3];
         V3<T> traw = vzero<T>();
+        const M3<T> Mw = qmat(qw);
 PPR_UNROLL
         for (int k = 0; k < 3; ++k) {
-            aw[k] = qrot(qw, ax[k]);
+            aw[k] = mrot(Mw, ax[k]);
             qd[k] = dot(aw[k], w_err);
             sc[k] = c.ke[k] * (ang[k] - c.target[k]) + c.kd[k] * qd[k] + c.act[k] -
                     (LIMITS ? joint_limit_force(ang[k], qd[k], c.lo[k], c.hi[k], c.lke[k], c.lkd[k]) : T(0));
@@ -384,7 +391,7 @@ PPR_UNROLL
         V3<T> gtr = clamp3_mask(traw, T(1e4), gt);
         T g_ang[3] = {T(0), T(0), T(0)};
         V3<T> g_ax[3] = {vzero<T>(), vzero<T>(), vzero<T>()};
-        Q4<T> g_qw = qzero<T>();
+        M3<T> Gw = m3_zero<T>();
 PPR_UNROLL
         for (int k = 0; k < 3; ++k) {
             T g_sc = dot(gtr, aw[k]);
@@ -393,9 +400,10 @@ PPR_UNROLL
             joint_scalar_adj<T, LIMITS>(ang[k], qd[k], c, k, g_sc, g_ang[k], g_qd, adj_target, adj_act, adj_ke, adj_kd);
             g_aw += w_err * g_qd;
             g_werr += aw[k] * g_qd;
-            g_qw += qrot_adj_q(qw, ax[k], g_aw);
-            g_ax[k] += qrot_inv(qw, g_aw);
+            m3_acc(Gw, g_aw, ax[k]);
+            g_ax[k] += mrot_t(Mw, g_aw);
         }
+        Q4<T> g_qw = qmat_adj(qw, Gw);
         Q4<T> g_qpc = compound_decompose_adj(q_pc, dec, g_ax[1], g_ax[2], g_ang);
         // q_pc = (conj(qoff) * r_err) * qoff ; qw = qA * qoff
         if (QOFF) {
@@ -463,14 +471,14 @@ PPR_UNROLL
 
 // ------------------------------------------------------------------------------------------ integrate (K5)
 template <class T>
-PPR_HD Body<T> integrate_fwd(const Body<T>& b, V3<T> xc, V3<T> com, const Wrench<T>& F, T inv_m, const T* I,
-                             const T* inv_I, V3<T> g, T dt) {
+PPR_HD Body<T> integrate_fwd(const Body<T>& b, const M3<T>& Rb, V3<T> xc, V3<T> com, const Wrench<T>& F, T inv_m,
+                             const T* I, const T* inv_I, V3<T> g, T dt) {
     T nz = inv_m != T(0) ? T(1) : T(0);
     V3<T> v1 = b.v + (F.f * inv_m + g * nz) * dt;
     V3<T> x1c = xc + v1 * dt;
-    V3<T> wb = qrot_inv(b.r, b.w);
-    V3<T> tb = qrot_inv(b.r, F.t) - cross(wb, matvec(I, wb));
-    V3<T> w1 = qrot(b.r, wb + matvec(inv_I, tb) * dt);
+    V3<T> wb = mrot_t(Rb, b.w);
+    V3<T> tb = mrot_t(Rb, F.t) - cross(wb, matvec(I, wb));
+    V3<T> w1 = mrot(Rb, wb + matvec(inv_I, tb) * dt);
     Q4<T> rq = b.r + qmul(q4<T>(w1.x, w1.y, w1.z, T(0)), b.r) * (T(0.5) * dt);
     T len;
     Q4<T> r1 = qnormalize(rq, len);
@@ -486,17 +494,18 @@ PPR_HD Body<T> integrate_fwd(const Body<T>& b, V3<T> xc, V3<T> com, const Wrench
 //   adj_I += gI_a (x) gI_b ,  adj_inv_I += giI_a (x) giI_b      (giI_a already carries the factor dt)
 // so that a caller can accumulate them wherever it likes (the CUDA adjoint keeps the accumulators in shared memory).
 template <class T>
-PPR_HD void integrate_adj_core(const Body<T>& b, V3<T> xc, V3<T> com, const Wrench<T>& F, T inv_m, const T* I,
-                               const T* inv_I, V3<T> g, T dt, const Body<T>& adjO, Body<T>& adjB, V3<T>& adj_xc,
-                               Wrench<T>& adjF, T& adj_inv_m, V3<T>& gI_a, V3<T>& gI_b, V3<T>& giI_a, V3<T>& giI_b) {
+PPR_HD void integrate_adj_core(const Body<T>& b, const M3<T>& Rb, V3<T> xc, V3<T> com, const Wrench<T>& F, T inv_m,
+                               const T* I, const T* inv_I, V3<T> g, T dt, const Body<T>& adjO, Body<T>& adjB, M3<T>& G,
+                               V3<T>& adj_xc, Wrench<T>& adjF, T& adj_inv_m, V3<T>& gI_a, V3<T>& gI_b, V3<T>& giI_a,
+                               V3<T>& giI_b) {
     // ---- recompute
     T nz = inv_m != T(0) ? T(1) : T(0);
     V3<T> v1 = b.v + (F.f * inv_m + g * nz) * dt;
-    V3<T> wb = qrot_inv(b.r, b.w);
+    V3<T> wb = mrot_t(Rb, b.w);
     V3<T> Iwb = matvec(I, wb);
-    V3<T> tb = qrot_inv(b.r, F.t) - cross(wb, Iwb);
+    V3<T> tb = mrot_t(Rb, F.t) - cross(wb, Iwb);
     V3<T> wb2 = wb + matvec(inv_I, tb) * dt;
-    V3<T> w1 = qrot(b.r, wb2);
+    V3<T> w1 = mrot(Rb, wb2);
     Q4<T> wq = q4<T>(w1.x, w1.y, w1.z, T(0));
     Q4<T> rq = b.r + qmul(wq, b.r) * (T(0.5) * dt);
     T len;
@@ -512,20 +521,20 @@ PPR_HD void integrate_adj_core(const Body<T>& b, V3<T> xc, V3<T> com, const Wren
     adjB.r += g_rq + qmul(qconj(wq), g_rq) * hdt;
     Q4<T> g_wq = qmul(g_rq, qconj(b.r)) * hdt;
     g_w1 += qvec(g_wq);
-    adjB.r += qrot_adj_q(b.r, wb2, g_w1);
-    V3<T> g_wb2 = qrot_inv(b.r, g_w1);
+    m3_acc(G, g_w1, wb2);
+    V3<T> g_wb2 = mrot_t(Rb, g_w1);
     V3<T> g_wb = g_wb2;
     V3<T> g_tb = matTvec(inv_I, g_wb2) * dt;
     giI_a = g_wb2 * dt; giI_b = tb;
-    adjF.t = qrot(b.r, g_tb);
-    adjB.r += qrotinv_adj_q(b.r, F.t, g_tb);
+    adjF.t = mrot(Rb, g_tb);
+    m3_acc(G, F.t, g_tb);
     V3<T> g_c = -g_tb;  // c = wb x Iwb
     g_wb += cross(Iwb, g_c);
     V3<T> g_Iwb = cross(g_c, wb);
     g_wb += matTvec(I, g_Iwb);
     gI_a = g_Iwb; gI_b = wb;
-    adjB.w += qrot(b.r, g_wb);
-    adjB.r += qrotinv_adj_q(b.r, b.w, g_wb);
+    adjB.w += mrot(Rb, g_wb);
+    m3_acc(G, b.w, g_wb);
     adj_xc += g_x1c;
     adjB.v += g_v1;
     V3<T> g_a = g_v1 * dt;
@@ -534,11 +543,11 @@ PPR_HD void integrate_adj_core(const Body<T>& b, V3<T> xc, V3<T> com, const Wren
 }
 
 template <class T>
-PPR_HD void integrate_adj(const Body<T>& b, V3<T> xc, V3<T> com, const Wrench<T>& F, T inv_m, const T* I,
-                          const T* inv_I, V3<T> g, T dt, const Body<T>& adjO, Body<T>& adjB, V3<T>& adj_xc,
-                          Wrench<T>& adjF, T& adj_inv_m, T* adj_I, T* adj_inv_I) {
+PPR_HD void integrate_adj(const Body<T>& b, const M3<T>& Rb, V3<T> xc, V3<T> com, const Wrench<T>& F, T inv_m,
+                          const T* I, const T* inv_I, V3<T> g, T dt, const Body<T>& adjO, Body<T>& adjB, M3<T>& G,
+                          V3<T>& adj_xc, Wrench<T>& adjF, T& adj_inv_m, T* adj_I, T* adj_inv_I) {
     V3<T> a, bb, c, d;
-    integrate_adj_core(b, xc, com, F, inv_m, I, inv_I, g, dt, adjO, adjB, adj_xc, adjF, adj_inv_m, a, bb, c, d);
+    integrate_adj_core(b, Rb, xc, com, F, inv_m, I, inv_I, g, dt, adjO, adjB, G, adj_xc, adjF, adj_inv_m, a, bb, c, d);
     outer_acc(adj_I, a, bb, T(1));
     outer_acc(adj_inv_I, c, d, T(1));
 }

@@ -26,6 +26,7 @@ typedef V3<float> F3;
 typedef Q4<float> F4;
 typedef Body<float> BodyF;
 typedef Wrench<float> WrenchF;
+typedef M3<float> M3F;
 
 #define PPR_MAX_CHILD 8
 #define PPR_CKPT_FLOATS 24  // body_q 7 + body_qd 6 + total wrench 6 + active-contact record 5 (count, 8 x u16)
@@ -272,8 +273,8 @@ __device__ __forceinline__ int rec_get(const ContactRec& r, unsigned i) {
 }
 
 // K3 for the whole warp: subtracts contact wrenches from F (per lane = per body)
-__device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
-                                                  const ContactMat<float>& cm0, const volatile float* st,
+__device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
+                                                  const M3F& Rb, F3 xc, const ContactMat<float>& cm0, const volatile float* st,
                                                   int* __restrict__ clist, WrenchF& F, ContactRec& rec) {
     float m0, m1, m2;
     int cand = contact_candidates(M, L, lane, s, st, clist, m0, m1, m2);
@@ -283,13 +284,13 @@ __device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneI
         for (int k = L.c0; k < L.c1; ++k) {
             float4 p = M.cpt[k];
             if (s.x.y + m0 * p.x + m1 * p.y + m2 * p.z - p.w > 1e-6f) continue;  // cheap conservative reject
-            if (contact_point_fwd(s, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), F)) rec_push(rec, k);
+            if (contact_point_fwd(s, Rb, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), F)) rec_push(rec, k);
         }
     } else {
         for (int i = 0; i < cand; ++i) {
             int k = clist[lane * PPR_CLIST_STRIDE + i];
             float4 p = M.cpt[k];
-            if (contact_point_fwd(s, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), F)) rec_push(rec, k);
+            if (contact_point_fwd(s, Rb, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), F)) rec_push(rec, k);
         }
     }
     if (cand == -1 || !can_rec) rec.cnt = PPR_REC_MAX + 1;
@@ -301,9 +302,10 @@ __device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneI
         F3 xca = shf3(xc, a);
         int c0 = __shfl_sync(FULL, L.c0, a), c1 = __shfl_sync(FULL, L.c1, a);
         WrenchF W = wrench_zero<float>();
+        const M3F Ra = qmat(sa.r);
         for (int k = c0 + lane; k < c1; k += 32) {
             float4 p = M.cpt[k];
-            contact_point_fwd(sa, xca, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), W);
+            contact_point_fwd(sa, Ra, xca, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), W);
         }
         W.t.x = warp_sum(W.t.x); W.t.y = warp_sum(W.t.y); W.t.z = warp_sum(W.t.z);
         W.f.x = warp_sum(W.f.x); W.f.y = warp_sum(W.f.y); W.f.z = warp_sum(W.f.z);
@@ -314,16 +316,17 @@ __device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneI
 
 // K3^T for the whole warp. Normally only replays the points the forward pass recorded as active; lanes whose
 // record overflowed (> PPR_REC_MAX active points) re-derive them like the forward pass did.
-__device__ __forceinline__ void warp_contacts_adj(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
-                                                  const ContactMat<float>& cm0, const volatile float* st,
-                                                  int* __restrict__ clist, const ContactRec& rec, const WrenchF& adjF,
-                                                  BodyF& adjS, F3& adj_xc) {
+__device__ __forceinline__ void warp_contacts_adj(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
+                                                  const M3F& Rb, F3 xc, const ContactMat<float>& cm0,
+                                                  const volatile float* st, int* __restrict__ clist,
+                                                  const ContactRec& rec, const WrenchF& adjF, BodyF& adjS, M3F& G,
+                                                  F3& adj_xc) {
     const bool ovf = L.valid && rec.cnt > PPR_REC_MAX;
     if (!ovf && L.valid) {
         for (unsigned i = 0; i < rec.cnt; ++i) {
             int k = rec_get(rec, i);
             float4 p = M.cpt[k];
-            contact_point_adj(s, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), adjF, adjS, adj_xc);
+            contact_point_adj(s, Rb, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), adjF, adjS, G, adj_xc);
         }
     }
     if (!__any_sync(FULL, ovf)) return;
@@ -333,13 +336,13 @@ __device__ __forceinline__ void warp_contacts_adj(const DevModel& M, const LaneI
     if (cand == -2) {
         for (int k = L.c0; k < L.c1; ++k) {
             float4 p = M.cpt[k];
-            contact_point_adj(s, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), adjF, adjS, adj_xc);
+            contact_point_adj(s, Rb, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), adjF, adjS, G, adj_xc);
         }
     } else {
         for (int i = 0; i < cand; ++i) {
             int k = clist[lane * PPR_CLIST_STRIDE + i];
             float4 p = M.cpt[k];
-            contact_point_adj(s, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), adjF, adjS, adj_xc);
+            contact_point_adj(s, Rb, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), adjF, adjS, G, adj_xc);
         }
     }
     unsigned mask = __ballot_sync(FULL, cand == -1);
@@ -352,10 +355,13 @@ __device__ __forceinline__ void warp_contacts_adj(const DevModel& M, const LaneI
         int c0 = __shfl_sync(FULL, L.c0, a), c1 = __shfl_sync(FULL, L.c1, a);
         BodyF A = body_zero<float>();
         F3 Axc = vzero<float>();
+        const M3F Ra = qmat(sa.r);
+        M3F Ga = m3_zero<float>();
         for (int k = c0 + lane; k < c1; k += 32) {
             float4 p = M.cpt[k];
-            contact_point_adj(sa, xca, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), aFa, A, Axc);
+            contact_point_adj(sa, Ra, xca, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), aFa, A, Ga, Axc);
         }
+        A.r += qmat_adj(sa.r, Ga);
         A.x.x = warp_sum(A.x.x); A.x.y = warp_sum(A.x.y); A.x.z = warp_sum(A.x.z);
         A.r.x = warp_sum(A.r.x); A.r.y = warp_sum(A.r.y); A.r.z = warp_sum(A.r.z); A.r.w = warp_sum(A.r.w);
         A.w.x = warp_sum(A.w.x); A.w.y = warp_sum(A.w.y); A.w.z = warp_sum(A.w.z);
@@ -494,8 +500,8 @@ __device__ __forceinline__ void store_wrench_row(float* base, const WrenchF& w) 
 
 // forces of one substep; F = total wrench on this lane's body. Optionally exports the grf / jaf side channels.
 template <int JM, bool LIMITS, bool QOFF>
-__device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s, F3 xc,
-                                            const JointCtl<float>& ctl, const ContactMat<float>& cm0,
+__device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
+                                            const M3F& Rb, F3 xc, const JointCtl<float>& ctl, const ContactMat<float>& cm0,
                                             const volatile float* st, int* clist, const float* res_f_row,
                                             float* grf_row, float* jaf_row, WrenchF& F, ContactRec& rec) {
     F = wrench_zero<float>();
@@ -503,7 +509,7 @@ __device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L
         F.t = v3<float>(res_f_row[0], res_f_row[1], res_f_row[2]);
         F.f = v3<float>(res_f_row[3], res_f_row[4], res_f_row[5]);
     }
-    warp_contacts_fwd(M, L, lane, s, xc, cm0, st, clist, F, rec);
+    warp_contacts_fwd(M, L, lane, s, Rb, xc, cm0, st, clist, F, rec);
     WrenchF G = F;
     if (grf_row && L.valid) store_wrench_row(grf_row, F);
     // joints: this lane is the child of its joint
@@ -512,7 +518,7 @@ __device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L
     if (!L.has_parent) { P = body_identity<float>(); xcp = vzero<float>(); }
     F3 t, f, ap, ac;
     joint_fwd<float, JM, LIMITS, QOFF>(st_joint<QOFF>(st, L.body, L.type), ctl, M.ake, M.akd, P, xcp, L.has_parent, s,
-                                       xc, t, f, ap, ac);
+                                       Rb, xc, t, f, ap, ac);
     WrenchF Wp = wrench_zero<float>();
     if (L.type != JT_FREE) {
         F.t -= t + cross(ac, f); F.f -= f;
@@ -594,11 +600,12 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         // when nobody asked for them
         if (t == A.nsteps - 1 && !A.out_grf && !A.out_jaf) break;
         const F3 com = st_vec3(st, ST_COM, L.body);
-        F3 xc = s.x + qrot(s.r, com);
+        const M3F Rb = qmat(s.r);
+        F3 xc = s.x + mrot(Rb, com);
         load_ctl(M, L, A, t, ke, kd, ctl);
         WrenchF F;
         ContactRec rec;
-        warp_forces<JM, LIMITS, QOFF>(M, L, lane, s, xc, ctl, cm0, st, clist, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
+        warp_forces<JM, LIMITS, QOFF>(M, L, lane, s, Rb, xc, ctl, cm0, st, clist, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
                     (frame && A.out_grf) ? A.out_grf + frow * 6 : nullptr,
                     (frame && A.out_jaf) ? A.out_jaf + frow * 6 : nullptr, F, rec);
         // checkpoint (coalesced: component-major rows of 32 lanes)
@@ -616,7 +623,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
             float I[9], inv_I[9];
             par_load9(par, 1, I);
             par_load9(par, 10, inv_I);
-            s = integrate_fwd(s, xc, com, F, par[0], I, inv_I, g, A.dt);
+            s = integrate_fwd(s, Rb, xc, com, F, par[0], I, inv_I, g, A.dt);
         }
     }
 }
@@ -721,7 +728,9 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
             cp_async_commit();
         }
         const F3 com = st_vec3(st, ST_COM, L.body);
-        F3 xc = s.x + qrot(s.r, com);
+        const M3F Rb = qmat(s.r);
+        M3F G = m3_zero<float>();   // dL/dRb, converted to the quaternion adjoint once at the end of the substep
+        F3 xc = s.x + mrot(Rb, com);
         load_ctl(M, L, A, tp, ke, kd, ctl);
         // K5^T
         BodyF adjS = body_zero<float>();
@@ -732,8 +741,8 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
             par_load9(par, 1, I);
             par_load9(par, 10, inv_I);
             F3 ga, gb, gc, gd;
-            integrate_adj_core(s, xc, com, F, par[0], I, inv_I, g, A.dt, adjN, adjS, adj_xc, adjF, a_inv_m, ga, gb, gc,
-                               gd);
+            integrate_adj_core(s, Rb, xc, com, F, par[0], I, inv_I, g, A.dt, adjN, adjS, G, adj_xc, adjF, a_inv_m, ga,
+                               gb, gc, gd);
             const float av[3] = {ga.x, ga.y, ga.z}, bv[3] = {gb.x, gb.y, gb.z};
             const float cv[3] = {gc.x, gc.y, gc.z}, dv[3] = {gd.x, gd.y, gd.z};
 #pragma unroll
@@ -753,7 +762,8 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         F3 adj_xcp = vzero<float>();
         float g_target[3] = {0, 0, 0}, g_act[3] = {0, 0, 0};
         joint_adj<float, JM, LIMITS, QOFF>(st_joint<QOFF>(st, L.body, L.type), ctl, M.ake, M.akd, P, xcp, L.has_parent, s,
-                                           xc, adjFp, adjF, adjP, adj_xcp, adjS, adj_xc, g_target, g_act, a_ke, a_kd);
+                                           Rb, xc, adjFp, adjF, adjP, adj_xcp, adjS, G, adj_xc, g_target, g_act, a_ke,
+                                           a_kd);
         adjP.x += adj_xcp;
         adjP.r += qrot_adj_q(P.r, st_vec3(st, ST_CPAR, L.body), adj_xcp);
         if (!L.has_parent) adjP = body_zero<float>();
@@ -771,7 +781,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
             }
         }
         // K3^T
-        warp_contacts_adj(M, L, lane, s, xc, cm0, st, clist, rec, adjF, adjS, adj_xc);
+        warp_contacts_adj(M, L, lane, s, Rb, xc, cm0, st, clist, rec, adjF, adjS, G, adj_xc);
         // K2^T
         if (A.adj_res_f && L.valid) {
             float* r = A.adj_res_f + ((tp * A.bs + L.env) * M.nb + L.body) * 6;
@@ -780,7 +790,8 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         }
         // world COM -> pose
         adjS.x += adj_xc;
-        adjS.r += qrot_adj_q(s.r, com, adj_xc);
+        m3_acc(G, adj_xc, com);
+        adjS.r += qmat_adj(s.r, G);
         adjN = adjS;
     }
     // K1^T: state 0 = eval_fk(q_init, qd_init), recomputed

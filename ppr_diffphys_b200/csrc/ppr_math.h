@@ -87,6 +87,49 @@ template <class T> PPR_HD Q4<T> qrotinv_adj_q(Q4<T> q, V3<T> v, V3<T> g) {
                  -tw * vxg.z + T(2) * (uv * g.z + ug * v.z), aw);
 }
 
+// ---- the same rotation as a 3x3 matrix -------------------------------------------------------------------
+// quat_rotate(q, v) is LINEAR in v for any (also non-unit) q:  M(q) = (2w^2-1) I + 2w [u]x + 2 u u^T.
+// A body that rotates many vectors by its own quaternion per substep builds M once (18 flops) and pays 9 flops per
+// rotation instead of ~21; in the adjoint every d/dq of such a rotation becomes a rank-1 update of G = dL/dM
+// (9 flops) and ONE conversion G -> dL/dq per body and substep (qmat_adj) instead of ~35 flops per rotation.
+template <class T> struct M3 { T m[9]; };  // row-major
+template <class T> PPR_HD M3<T> m3_zero() { M3<T> r; PPR_UNROLL for (int i = 0; i < 9; ++i) r.m[i] = T(0); return r; }
+template <class T> PPR_HD M3<T> qmat(Q4<T> q) {
+    T a = T(2) * q.w * q.w - T(1), tw = T(2) * q.w;
+    T xx = T(2) * q.x * q.x, yy = T(2) * q.y * q.y, zz = T(2) * q.z * q.z;
+    T xy = T(2) * q.x * q.y, xz = T(2) * q.x * q.z, yz = T(2) * q.y * q.z;
+    M3<T> r;
+    r.m[0] = a + xx;        r.m[1] = xy - tw * q.z; r.m[2] = xz + tw * q.y;
+    r.m[3] = xy + tw * q.z; r.m[4] = a + yy;        r.m[5] = yz - tw * q.x;
+    r.m[6] = xz - tw * q.y; r.m[7] = yz + tw * q.x; r.m[8] = a + zz;
+    return r;
+}
+template <class T> PPR_HD V3<T> mrot(const M3<T>& M, V3<T> v) {   // = quat_rotate(q, v)
+    return v3<T>(M.m[0] * v.x + M.m[1] * v.y + M.m[2] * v.z, M.m[3] * v.x + M.m[4] * v.y + M.m[5] * v.z,
+                 M.m[6] * v.x + M.m[7] * v.y + M.m[8] * v.z);
+}
+template <class T> PPR_HD V3<T> mrot_t(const M3<T>& M, V3<T> v) { // = quat_rotate_inv(q, v)
+    return v3<T>(M.m[0] * v.x + M.m[3] * v.y + M.m[6] * v.z, M.m[1] * v.x + M.m[4] * v.y + M.m[7] * v.z,
+                 M.m[2] * v.x + M.m[5] * v.y + M.m[8] * v.z);
+}
+// adjoint bookkeeping: y = M v  with adjoint g  ->  G += g v^T ;   y = M^T v with adjoint g  ->  G += v g^T
+template <class T> PPR_HD void m3_acc(M3<T>& G, V3<T> a, V3<T> b) {  // G += a b^T
+    G.m[0] += a.x * b.x; G.m[1] += a.x * b.y; G.m[2] += a.x * b.z;
+    G.m[3] += a.y * b.x; G.m[4] += a.y * b.y; G.m[5] += a.y * b.z;
+    G.m[6] += a.z * b.x; G.m[7] += a.z * b.y; G.m[8] += a.z * b.z;
+}
+// dL/dq from G = dL/dM(q)
+template <class T> PPR_HD Q4<T> qmat_adj(Q4<T> q, const M3<T>& G) {
+    T ax = G.m[7] - G.m[5], ay = G.m[2] - G.m[6], az = G.m[3] - G.m[1];   // a_k = sum_ij eps_ikj G_ij
+    T tr = G.m[0] + G.m[4] + G.m[8];
+    T sx = (G.m[0] + G.m[0]) * q.x + (G.m[1] + G.m[3]) * q.y + (G.m[2] + G.m[6]) * q.z;  // ((G + G^T) u)
+    T sy = (G.m[3] + G.m[1]) * q.x + (G.m[4] + G.m[4]) * q.y + (G.m[5] + G.m[7]) * q.z;
+    T sz = (G.m[6] + G.m[2]) * q.x + (G.m[7] + G.m[5]) * q.y + (G.m[8] + G.m[8]) * q.z;
+    T tw = T(2) * q.w;
+    return q4<T>(tw * ax + T(2) * sx, tw * ay + T(2) * sy, tw * az + T(2) * sz,
+                 T(4) * q.w * tr + T(2) * (q.x * ax + q.y * ay + q.z * az));
+}
+
 template <class T> PPR_HD Q4<T> q_axis_angle(V3<T> a, T ang) {
     T h = T(0.5) * ang, s = sin(h), c = cos(h);
     return q4<T>(a.x * s, a.y * s, a.z * s, c);
