@@ -203,15 +203,21 @@ template <class T> struct CompoundDec {
     T sa0, ca0, sa1, ca1;
     V3<T> e1, e2;
 };
-template <class T> PPR_HD CompoundDec<T> compound_decompose(Q4<T> q_pc) {
+// `known` (optional): the three angles as computed by an earlier call on the same q_pc (the forward kernel stores them
+// in the checkpoint so that the adjoint kernel does not repeat the two atan2 and the asin).
+template <class T> PPR_HD CompoundDec<T> compound_decompose(Q4<T> q_pc, const T* known = nullptr) {
     CompoundDec<T> d;
     V3<T> c0 = qrot(q_pc, v3<T>(T(1), T(0), T(0)));
     V3<T> c1 = qrot(q_pc, v3<T>(T(0), T(1), T(0)));
     d.c2 = qrot(q_pc, v3<T>(T(0), T(0), T(1)));
     d.c0x = c0.x; d.c1x = c1.x;
-    d.ang[0] = -atan2(d.c2.y, d.c2.z);
-    d.ang[1] = -safe_asin(-d.c2.x);
-    d.ang[2] = -atan2(d.c1x, d.c0x);
+    if (known) {
+        d.ang[0] = known[0]; d.ang[1] = known[1]; d.ang[2] = known[2];
+    } else {
+        d.ang[0] = -atan2(d.c2.y, d.c2.z);
+        d.ang[1] = -safe_asin(-d.c2.x);
+        d.ang[2] = -atan2(d.c1x, d.c0x);
+    }
     T rho = sqrt(d.c2.y * d.c2.y + d.c2.z * d.c2.z);
     if (rho > T(0)) { T ir = T(1) / rho; d.ca0 = d.c2.z * ir; d.sa0 = -d.c2.y * ir; }
     else { d.ca0 = T(1); d.sa0 = T(0); }  // atan2(0,0) = 0
@@ -244,8 +250,9 @@ template <class T> PPR_HD Q4<T> compound_decompose_adj(Q4<T> q_pc, const Compoun
 template <class T, int JM = JM_ALL, bool LIMITS = true, bool QOFF = true>
 PPR_HD void joint_fwd(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T akd, const Body<T>& P, V3<T> xcp,
                       bool has_parent, const Body<T>& C, const M3<T>& Rc, V3<T> xcc, V3<T>& t_out, V3<T>& f_out,
-                      V3<T>& arm_p, V3<T>& arm_c) {
+                      V3<T>& arm_p, V3<T>& arm_c, T* ang_out = nullptr) {
     t_out = vzero<T>(); f_out = vzero<T>();
+    if (ang_out) { ang_out[0] = T(0); ang_out[1] = T(0); ang_out[2] = T(0); }
     V3<T> xA = P.x + qrot(P.r, js.xpj);
     Q4<T> qA = qmul(P.r, js.qpj);
     arm_p = has_parent ? xA - xcp : vzero<T>();
@@ -258,6 +265,7 @@ PPR_HD void joint_fwd(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
     if (JM != JM_COMPOUND && js.type == JT_REVOLUTE) {
         V3<T> axis_p = qrot(qA, js.axis), axis_c = mrot(Rc, js.axis);
         T q = revolute_angle(js.axis, r_err);
+        if (ang_out) ang_out[0] = q;
         T qd = dot(w_err, axis_p);
         T sc = c.ke[0] * (q - c.target[0]) + c.kd[0] * qd + c.act[0] -
                (LIMITS ? joint_limit_force(q, qd, c.lo[0], c.hi[0], c.lke[0], c.lkd[0]) : T(0));
@@ -267,6 +275,7 @@ PPR_HD void joint_fwd(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
         Q4<T> q_pc = QOFF ? qmul(qmul(qconj(js.qoff), r_err), js.qoff) : r_err;
         CompoundDec<T> dec = compound_decompose(q_pc);
         const T* ang = dec.ang;
+        if (ang_out) { ang_out[0] = ang[0]; ang_out[1] = ang[1]; ang_out[2] = ang[2]; }
         Q4<T> qw = QOFF ? qmul(qA, js.qoff) : qA;
         V3<T> ax[3] = {v3<T>(T(1), T(0), T(0)), dec.e1, dec.e2};
         const M3<T> Mw = qmat(qw);
@@ -299,7 +308,7 @@ template <class T, int JM = JM_ALL, bool LIMITS = true, bool QOFF = true>
 PPR_HD void joint_adj(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T akd, const Body<T>& P, V3<T> xcp,
                       bool has_parent, const Body<T>& C, const M3<T>& Rc, V3<T> xcc, const Wrench<T>& adjFp,
                       const Wrench<T>& adjFc, Body<T>& adjP, V3<T>& adj_xcp, Body<T>& adjC, M3<T>& Gc, V3<T>& adj_xcc,
-                      T* adj_target, T* adj_act, T* adj_ke, T* adj_kd) {
+                      T* adj_target, T* adj_act, T* adj_ke, T* adj_kd, const T* ang_in = nullptr) {
     if (js.type == JT_FREE) return;
     // ---- recompute forward
     V3<T> xA = P.x + qrot(P.r, js.xpj);
@@ -324,7 +333,7 @@ PPR_HD void joint_adj(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
 
     if (JM != JM_COMPOUND && js.type == JT_REVOLUTE) {
         V3<T> axis_p = qrot(qA, js.axis), axis_c = mrot(Rc, js.axis);
-        T q = revolute_angle(js.axis, r_err);
+        T q = ang_in ? ang_in[0] : revolute_angle(js.axis, r_err);
         T qd = dot(w_err, axis_p);
         T sc = c.ke[0] * (q - c.target[0]) + c.kd[0] * qd + c.act[0] -
                (LIMITS ? joint_limit_force(q, qd, c.lo[0], c.hi[0], c.lke[0], c.lkd[0]) : T(0));
@@ -365,7 +374,7 @@ PPR_HD void joint_adj(const JointStatic<T>& js, const JointCtl<T>& c, T ake, T a
     if (JM != JM_REVOLUTE && js.type == JT_COMPOUND) {
         Q4<T> q_pc = QOFF ? qmul(qmul(qconj(js.qoff), r_err), js.qoff) : r_err;
         const V3<T> ex = v3<T>(T(1), T(0), T(0));
-        CompoundDec<T> dec = compound_decompose(q_pc);
+        CompoundDec<T> dec = compound_decompose(q_pc, ang_in);
         const T* ang = dec.ang;
         Q4<T> qw = QOFF ? qmul(qA, js.qoff) : qA;
         V3<T> ax[3] = {ex, dec.e1, dec.e2};

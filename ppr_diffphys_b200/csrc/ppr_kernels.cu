@@ -29,7 +29,8 @@ typedef Wrench<float> WrenchF;
 typedef M3<float> M3F;
 
 #define PPR_MAX_CHILD 8
-#define PPR_CKPT_FLOATS 24  // body_q 7 + body_qd 6 + total wrench 6 + active-contact record 5 (count, 8 x u16)
+#define PPR_CKPT_FLOATS 28  // body_q 7 + body_qd 6 + total wrench 6 + active-contact record 5 (count, 8 x u16) +
+                           // joint angles 3 + pad 1 (rows stay a multiple of 32 x 16 bytes)
 #define PPR_REC_MAX 8
 #define PPR_BLOCK 128
 #define PPR_WARPS (PPR_BLOCK / 32)
@@ -503,7 +504,7 @@ template <int JM, bool LIMITS, bool QOFF>
 __device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
                                             const M3F& Rb, F3 xc, const JointCtl<float>& ctl, const ContactMat<float>& cm0,
                                             const volatile float* st, int* clist, const float* res_f_row,
-                                            float* grf_row, float* jaf_row, WrenchF& F, ContactRec& rec) {
+                                            float* grf_row, float* jaf_row, WrenchF& F, ContactRec& rec, float* ang) {
     F = wrench_zero<float>();
     if (res_f_row && L.valid) {
         F.t = v3<float>(res_f_row[0], res_f_row[1], res_f_row[2]);
@@ -518,7 +519,7 @@ __device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L
     if (!L.has_parent) { P = body_identity<float>(); xcp = vzero<float>(); }
     F3 t, f, ap, ac;
     joint_fwd<float, JM, LIMITS, QOFF>(st_joint<QOFF>(st, L.body, L.type), ctl, M.ake, M.akd, P, xcp, L.has_parent, s,
-                                       Rb, xc, t, f, ap, ac);
+                                       Rb, xc, t, f, ap, ac, ang);
     WrenchF Wp = wrench_zero<float>();
     if (L.type != JT_FREE) {
         F.t -= t + cross(ac, f); F.f -= f;
@@ -605,9 +606,10 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         load_ctl(M, L, A, t, ke, kd, ctl);
         WrenchF F;
         ContactRec rec;
+        float ang[3];
         warp_forces<JM, LIMITS, QOFF>(M, L, lane, s, Rb, xc, ctl, cm0, st, clist, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
                     (frame && A.out_grf) ? A.out_grf + frow * 6 : nullptr,
-                    (frame && A.out_jaf) ? A.out_jaf + frow * 6 : nullptr, F, rec);
+                    (frame && A.out_jaf) ? A.out_jaf + frow * 6 : nullptr, F, rec, ang);
         // checkpoint (coalesced: component-major rows of 32 lanes)
         float* c = ck + t * ck_step;
         c[0 * 32] = s.x.x; c[1 * 32] = s.x.y; c[2 * 32] = s.x.z;
@@ -619,6 +621,8 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         c[19 * 32] = __uint_as_float(rec.cnt);
         c[20 * 32] = __uint_as_float((unsigned)rec.lo); c[21 * 32] = __uint_as_float((unsigned)(rec.lo >> 32));
         c[22 * 32] = __uint_as_float((unsigned)rec.hi); c[23 * 32] = __uint_as_float((unsigned)(rec.hi >> 32));
+        c[24 * 32] = ang[0];
+        if (JM != JM_REVOLUTE) { c[25 * 32] = ang[1]; c[26 * 32] = ang[2]; }
         {
             float I[9], inv_I[9];
             par_load9(par, 1, I);
@@ -722,6 +726,10 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         rec.cnt = __float_as_uint(row[19 * 32]);
         rec.lo = (unsigned long long)__float_as_uint(row[20 * 32]) | ((unsigned long long)__float_as_uint(row[21 * 32]) << 32);
         rec.hi = (unsigned long long)__float_as_uint(row[22 * 32]) | ((unsigned long long)__float_as_uint(row[23 * 32]) << 32);
+        float ang[3];
+        ang[0] = row[24 * 32];
+        ang[1] = JM != JM_REVOLUTE ? row[25 * 32] : 0.f;
+        ang[2] = JM != JM_REVOLUTE ? row[26 * 32] : 0.f;
         __syncwarp();        // everyone has read the row: refill it with the next (earlier) one
         if (tp > 0) {
             cp_async_row(roww, ckw + (tp - 1) * ck_step, lane);
@@ -763,7 +771,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         float g_target[3] = {0, 0, 0}, g_act[3] = {0, 0, 0};
         joint_adj<float, JM, LIMITS, QOFF>(st_joint<QOFF>(st, L.body, L.type), ctl, M.ake, M.akd, P, xcp, L.has_parent, s,
                                            Rb, xc, adjFp, adjF, adjP, adj_xcp, adjS, G, adj_xc, g_target, g_act, a_ke,
-                                           a_kd);
+                                           a_kd, ang);
         adjP.x += adj_xcp;
         adjP.r += qrot_adj_q(P.r, st_vec3(st, ST_CPAR, L.body), adj_xcp);
         if (!L.has_parent) adjP = body_zero<float>();
