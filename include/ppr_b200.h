@@ -65,8 +65,10 @@ int ppr_model_destroy(ppr_model_t m);
 int ppr_model_set_joint_X_p(ppr_model_t m, const float* joint_X_p, void* stream);
 int ppr_model_set_attach(ppr_model_t m, float attach_ke, float attach_kd);
 int ppr_model_set_gravity(ppr_model_t m, const float g[3]);
-/* introspection: environments packed per warp, lanes used per warp */
-int ppr_model_envs_per_warp(ppr_model_t m);
+/* introspection of the environment packing chosen for this articulation: a group is a warp (32 threads) or a
+ * thread block (96 / 160 threads); each group hosts floor(threads / nb) environments, one thread per body. */
+int ppr_model_envs_per_group(ppr_model_t m);
+int ppr_model_group_threads(ppr_model_t m);
 
 /* ---- articulation FK (replaces eval_fk launches at dp_model.py:1068 and its tape adjoint :1101) ------------
  * n = number of independent articulations (reference: T frames x bs envs, one launch per frame).

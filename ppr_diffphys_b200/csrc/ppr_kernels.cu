@@ -1,7 +1,10 @@
 // sm_100a kernels + C ABI of the rollout hot path (see include/ppr_b200.h for the boundary and the reference
 // call sites each entry point replaces).
 //
-// Mapping: one LANE per rigid body, floor(32/nb) environments per warp (laikago 2x13, human 1x19, quad 1x26).
+// Mapping: one THREAD per rigid body. Environments are packed either per WARP (floor(32/nb) envs per warp, tree
+// exchange by warp shuffles) or per BLOCK (floor(NT/nb) envs per block of NT threads, tree exchange through shared
+// memory + __syncthreads) -- whichever wastes fewer lanes: human has 19 bodies, i.e. 59 % lane use per warp but
+// 99 % with 5 envs in a 96-thread block. The two are the `Comm` policy of the kernels below.
 // The body state (13 floats) lives in registers for the whole rollout; parent/child exchange of states and
 // wrenches is done with warp shuffles on the static articulation tree (no shared memory, no atomics ->
 // deterministic, unlike the reference's atomic_add/sub at integrator_euler.py:179,449,451).  The time loop is
@@ -12,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -67,7 +71,10 @@ struct ppr_model {
     size_t xpj_offset;        // byte offset of xpj inside blob
     std::vector<float> h_xpj;
     int variant;              // 0: FREE+REVOLUTE, 1: FREE+COMPOUND (both: no limits, identity q_off), 2: generic
+    int comm;                 // env packing of the rollout kernels: 0 per warp (128-thread blocks), 1 per 96-thread
+                              // block, 2 per 160-thread block
 };
+static const int kCommThreads[3] = {128, 96, 160};
 #define PPR_MAGIC 0x50505231u
 
 // ----------------------------------------------------------------------------------------------- lane helpers
@@ -108,6 +115,141 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// ----------------------------------------------------------------------------------------------- tree exchange
+// Collectives over the articulation tree, executed by EVERY thread of the group (warp or block):
+//   parent_*  : each thread obtains values held by the thread of its parent body
+//   gather_*  : each thread sums a message held by the threads of its child bodies
+// `child` packs up to 8 child slots as bytes (0xff = none); `ps` = slot of the parent (own slot if none).
+template <int NT> struct WarpComm {
+    static constexpr int kThreads = NT;
+    static constexpr bool kBlock = false;
+    static constexpr int kExFloats = 0;
+    __device__ __forceinline__ explicit WarpComm(float*) {}
+    static __device__ __forceinline__ int64_t group() { return ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; }
+    static __device__ __forceinline__ int slot() { return threadIdx.x & 31; }
+    static __device__ __forceinline__ int envs_per_group(const DevModel& M) { return 32 / M.nb; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ BodyF parent_body(const BodyF& s, int ps) const { return shf_body(s, ps); }
+    __device__ __forceinline__ F3 parent_vec(F3 v, int ps) const { return shf3(v, ps); }
+    __device__ __forceinline__ void parent_state(const BodyF& s, F3 xc, int ps, BodyF& P, F3& xcp) const {
+        P = shf_body(s, ps); xcp = shf3(xc, ps);
+    }
+    __device__ __forceinline__ void parent_state_w(const BodyF& s, F3 xc, const WrenchF& w, int ps, BodyF& P, F3& xcp,
+                                                   WrenchF& wp) const {
+        P = shf_body(s, ps); xcp = shf3(xc, ps); wp = shf_wrench(w, ps);
+    }
+    __device__ __forceinline__ void gather_wrench(const WrenchF& mine, unsigned long long child, int maxc,
+                                                  WrenchF& acc) const {
+#pragma unroll 1
+        for (int sl = 0; sl < maxc; ++sl) {
+            unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
+            WrenchF o = shf_wrench(mine, c == 0xffu ? 0 : (int)c);
+            if (c != 0xffu) { acc.t += o.t; acc.f += o.f; }
+        }
+    }
+    __device__ __forceinline__ void gather_body(const BodyF& mine, unsigned long long child, int maxc, BodyF& acc) const {
+#pragma unroll 1
+        for (int sl = 0; sl < maxc; ++sl) {
+            unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
+            BodyF o = shf_body(mine, c == 0xffu ? 0 : (int)c);
+            if (c != 0xffu) body_acc(acc, o);
+        }
+    }
+};
+
+// Block-wide variant: values are published in shared memory ([component][thread], conflict-free), one
+// __syncthreads, then read at the partner's slot. In the substep loops a parent_state* call always alternates with
+// a gather_* call (different areas `ex` / `msg`), which makes the single barrier per call sufficient: every read of
+// an area happens before the next barrier, every write to it after one more barrier. parent_body / parent_vec are
+// used back to back (FK levels) and therefore carry a trailing barrier.
+template <int NT> struct BlockComm {
+    static constexpr int kThreads = NT;
+    static constexpr bool kBlock = true;
+    static constexpr int kExFloats = (22 + 13) * NT;
+    float* ex;   // [22][NT]
+    float* msg;  // [13][NT]
+    __device__ __forceinline__ explicit BlockComm(float* sm) : ex(sm), msg(sm + 22 * NT) {}
+    static __device__ __forceinline__ int64_t group() { return blockIdx.x; }
+    static __device__ __forceinline__ int slot() { return threadIdx.x; }
+    static __device__ __forceinline__ int envs_per_group(const DevModel& M) { return NT / M.nb; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void put_body(float* a, const BodyF& s) const {
+        const int t = threadIdx.x;
+        a[0 * NT + t] = s.x.x; a[1 * NT + t] = s.x.y; a[2 * NT + t] = s.x.z;
+        a[3 * NT + t] = s.r.x; a[4 * NT + t] = s.r.y; a[5 * NT + t] = s.r.z; a[6 * NT + t] = s.r.w;
+        a[7 * NT + t] = s.w.x; a[8 * NT + t] = s.w.y; a[9 * NT + t] = s.w.z;
+        a[10 * NT + t] = s.v.x; a[11 * NT + t] = s.v.y; a[12 * NT + t] = s.v.z;
+    }
+    __device__ __forceinline__ BodyF get_body(const float* a, int t) const {
+        BodyF o;
+        o.x = v3<float>(a[0 * NT + t], a[1 * NT + t], a[2 * NT + t]);
+        o.r = q4<float>(a[3 * NT + t], a[4 * NT + t], a[5 * NT + t], a[6 * NT + t]);
+        o.w = v3<float>(a[7 * NT + t], a[8 * NT + t], a[9 * NT + t]);
+        o.v = v3<float>(a[10 * NT + t], a[11 * NT + t], a[12 * NT + t]);
+        return o;
+    }
+    __device__ __forceinline__ BodyF parent_body(const BodyF& s, int ps) const {
+        put_body(ex, s);
+        __syncthreads();
+        BodyF o = get_body(ex, ps);
+        __syncthreads();
+        return o;
+    }
+    __device__ __forceinline__ F3 parent_vec(F3 v, int ps) const {
+        const int t = threadIdx.x;
+        ex[0 * NT + t] = v.x; ex[1 * NT + t] = v.y; ex[2 * NT + t] = v.z;
+        __syncthreads();
+        F3 o = v3<float>(ex[0 * NT + ps], ex[1 * NT + ps], ex[2 * NT + ps]);
+        __syncthreads();
+        return o;
+    }
+    __device__ __forceinline__ void parent_state(const BodyF& s, F3 xc, int ps, BodyF& P, F3& xcp) const {
+        const int t = threadIdx.x;
+        put_body(ex, s);
+        ex[13 * NT + t] = xc.x; ex[14 * NT + t] = xc.y; ex[15 * NT + t] = xc.z;
+        __syncthreads();
+        P = get_body(ex, ps);
+        xcp = v3<float>(ex[13 * NT + ps], ex[14 * NT + ps], ex[15 * NT + ps]);
+    }
+    __device__ __forceinline__ void parent_state_w(const BodyF& s, F3 xc, const WrenchF& w, int ps, BodyF& P, F3& xcp,
+                                                   WrenchF& wp) const {
+        const int t = threadIdx.x;
+        put_body(ex, s);
+        ex[13 * NT + t] = xc.x; ex[14 * NT + t] = xc.y; ex[15 * NT + t] = xc.z;
+        ex[16 * NT + t] = w.t.x; ex[17 * NT + t] = w.t.y; ex[18 * NT + t] = w.t.z;
+        ex[19 * NT + t] = w.f.x; ex[20 * NT + t] = w.f.y; ex[21 * NT + t] = w.f.z;
+        __syncthreads();
+        P = get_body(ex, ps);
+        xcp = v3<float>(ex[13 * NT + ps], ex[14 * NT + ps], ex[15 * NT + ps]);
+        wp.t = v3<float>(ex[16 * NT + ps], ex[17 * NT + ps], ex[18 * NT + ps]);
+        wp.f = v3<float>(ex[19 * NT + ps], ex[20 * NT + ps], ex[21 * NT + ps]);
+    }
+    __device__ __forceinline__ void gather_wrench(const WrenchF& mine, unsigned long long child, int maxc,
+                                                  WrenchF& acc) const {
+        const int t = threadIdx.x;
+        msg[0 * NT + t] = mine.t.x; msg[1 * NT + t] = mine.t.y; msg[2 * NT + t] = mine.t.z;
+        msg[3 * NT + t] = mine.f.x; msg[4 * NT + t] = mine.f.y; msg[5 * NT + t] = mine.f.z;
+        __syncthreads();
+#pragma unroll 1
+        for (int sl = 0; sl < maxc; ++sl) {
+            unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
+            if (c != 0xffu) {
+                acc.t += v3<float>(msg[0 * NT + c], msg[1 * NT + c], msg[2 * NT + c]);
+                acc.f += v3<float>(msg[3 * NT + c], msg[4 * NT + c], msg[5 * NT + c]);
+            }
+        }
+    }
+    __device__ __forceinline__ void gather_body(const BodyF& mine, unsigned long long child, int maxc, BodyF& acc) const {
+        put_body(msg, mine);
+        __syncthreads();
+#pragma unroll 1
+        for (int sl = 0; sl < maxc; ++sl) {
+            unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
+            if (c != 0xffu) body_acc(acc, get_body(msg, (int)c));
+        }
+    }
+};
+
 // Shared-memory residency of everything that is constant over the time loop, so that it does not occupy
 // registers for the whole rollout (the kernels are occupancy/latency bound):
 //   static per-BODY table  sm_st[PPR_NSTATIC][32]   (indexed by body; lanes of different envs broadcast-read)
@@ -120,25 +262,27 @@ __device__ __forceinline__ float warp_sum(float v) {
 enum { ST_XPJ = 0, ST_QPJ = 3, ST_AXIS = 7, ST_COM = 10, ST_CPAR = 13, ST_AABB = 16, ST_QOFF = 23 };
 
 struct LaneInfo {
-    int env, body, parent_lane, type, ndof, depth, qs, qds, c0, c1;
+    int env, body, parent_slot, type, ndof, depth, qs, qds, c0, c1;
     bool valid, has_parent;
-    unsigned long long child;  // lane ids of children (0xff none)
+    unsigned long long child;  // slots (lane / thread ids inside the group) of the children, one byte each, 0xff none
     JointStatic<float> js;
     F3 com;
     float aabb[7];
 };
 
-__device__ __forceinline__ LaneInfo lane_setup(const DevModel& M, int64_t warp, int lane, int64_t n_env) {
+// group = warp or block index, slot = lane or thread index inside it, epg = environments per group
+__device__ __forceinline__ LaneInfo lane_setup(const DevModel& M, int64_t group, int slot, int64_t n_env, int epg) {
     LaneInfo L;
-    int e_in_w = lane / M.nb;
-    int body = lane - e_in_w * M.nb;
-    int64_t env = warp * M.epw + e_in_w;
-    L.valid = (e_in_w < M.epw) && (env < n_env);
-    if (!L.valid) { e_in_w = 0; body = 0; env = warp * M.epw; }
+    const int lane = slot;
+    int e_in_w = slot / M.nb;
+    int body = slot - e_in_w * M.nb;
+    int64_t env = group * epg + e_in_w;
+    L.valid = (e_in_w < epg) && (env < n_env);
+    if (!L.valid) { e_in_w = 0; body = 0; env = group * epg; }
     int seg = e_in_w * M.nb;
     L.env = (int)env; L.body = body;
     int4 ji = M.jinfo[body], j2 = M.jinfo2[body];
-    L.type = ji.x; L.has_parent = ji.y >= 0; L.parent_lane = L.has_parent ? seg + ji.y : lane;
+    L.type = ji.x; L.has_parent = ji.y >= 0; L.parent_slot = L.has_parent ? seg + ji.y : lane;
     L.qs = ji.z; L.qds = ji.w; L.ndof = j2.x; L.depth = j2.y; L.c0 = j2.z; L.c1 = j2.w;
     unsigned long long ch = M.child[body], out = 0;
 #pragma unroll
@@ -189,9 +333,10 @@ __device__ __forceinline__ JointStatic<float> st_joint(const volatile float* st,
                    : q4<float>(0.f, 0.f, 0.f, 1.f);
     return js;
 }
+template <int NT>
 __device__ __forceinline__ void par_load9(const volatile float* par, int row0, float* out) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) out[i] = par[(row0 + i) * PPR_BLOCK];
+    for (int i = 0; i < 9; ++i) out[i] = par[(row0 + i) * NT];
 }
 
 __device__ __forceinline__ ContactMat<float> load_mat(const DevModel& M, int k) {
@@ -374,25 +519,16 @@ __device__ __forceinline__ void warp_contacts_adj(const DevModel& M, const LaneI
 }
 
 // articulation FK across the warp, level by level (parents before children)
-template <int JM>
-__device__ __forceinline__ BodyF warp_fk(const DevModel& M, const LaneInfo& L, const float* jq, const float* jqd) {
+template <int JM, class Comm>
+__device__ __forceinline__ BodyF warp_fk(const Comm& comm, const DevModel& M, const LaneInfo& L, const float* jq,
+                                         const float* jqd) {
     BodyF s = body_identity<float>();
     for (int d = 0; d <= M.maxdepth; ++d) {
-        BodyF P = shf_body(s, L.parent_lane);
+        BodyF P = comm.parent_body(s, L.parent_slot);
         if (!L.has_parent) P = body_identity<float>();
         if (L.depth == d) s = fk_joint_fwd<float, JM>(L.js, L.com, P, jq, jqd);
     }
     return s;
-}
-
-// sum over this lane's children of a Body-shaped quantity held by the child lanes
-__device__ __forceinline__ void gather_children_body(const DevModel& M, const LaneInfo& L, const BodyF& mine, BodyF& acc) {
-#pragma unroll 1
-    for (int sl = 0; sl < M.maxc; ++sl) {
-        unsigned c = (unsigned)((L.child >> (8 * sl)) & 0xffu);
-        BodyF o = shf_body(mine, c == 0xffu ? 0 : (int)c);
-        if (c != 0xffu) body_acc(acc, o);
-    }
 }
 
 __device__ __forceinline__ void load_joint_coords(const LaneInfo& L, const float* q, const float* qd, int nq, int nqd,
@@ -412,10 +548,11 @@ fk_forward_kernel(DevModel M, int64_t n, const float* __restrict__ q, const floa
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp * M.epw >= n) return;
-    LaneInfo L = lane_setup(M, warp, lane, n);
+    const WarpComm<PPR_BLOCK> comm(nullptr);
+    LaneInfo L = lane_setup(M, warp, lane, n, M.epw);
     float jq[7], jqd[6];
     load_joint_coords(L, q, qd, M.nq, M.nqd, jq, jqd);
-    BodyF s = warp_fk<JM>(M, L, jq, jqd);
+    BodyF s = warp_fk<JM>(comm, M, L, jq, jqd);
     if (L.valid) {
         float* o = body_q + ((int64_t)L.env * M.nb + L.body) * 7;
         o[0] = s.x.x; o[1] = s.x.y; o[2] = s.x.z; o[3] = s.r.x; o[4] = s.r.y; o[5] = s.r.z; o[6] = s.r.w;
@@ -425,17 +562,18 @@ fk_forward_kernel(DevModel M, int64_t n, const float* __restrict__ q, const floa
 }
 
 // shared by fk_backward_kernel and the tail of rollout_backward_kernel
-template <int JM>
-__device__ __forceinline__ void warp_fk_adjoint(const DevModel& M, const LaneInfo& L, const BodyF& s, BodyF adj,
-                                                const float* jq, const float* jqd, float* __restrict__ adj_q,
-                                                float* __restrict__ adj_qd) {
+template <int JM, class Comm>
+__device__ __forceinline__ void warp_fk_adjoint(const Comm& comm, const DevModel& M, const LaneInfo& L, const BodyF& s,
+                                                BodyF adj, const float* jq, const float* jqd,
+                                                float* __restrict__ adj_q, float* __restrict__ adj_qd) {
     float ajq[7] = {0, 0, 0, 0, 0, 0, 0}, ajqd[6] = {0, 0, 0, 0, 0, 0};
     for (int d = M.maxdepth; d >= 0; --d) {
-        BodyF P = shf_body(s, L.parent_lane);
+        BodyF P = comm.parent_body(s, L.parent_slot);
         if (!L.has_parent) P = body_identity<float>();
         BodyF adjP = body_zero<float>();
         if (L.depth == d) fk_joint_adj<float, JM>(L.js, L.com, P, jq, jqd, adj, adjP, ajq, ajqd);
-        gather_children_body(M, L, adjP, adj);
+        comm.gather_body(adjP, L.child, M.maxc, adj);
+        comm.sync();
     }
     if (L.valid) {
         int ncoord = L.type == JT_FREE ? 7 : L.ndof;
@@ -454,10 +592,11 @@ fk_backward_kernel(DevModel M, int64_t n, const float* __restrict__ q, const flo
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp * M.epw >= n) return;
-    LaneInfo L = lane_setup(M, warp, lane, n);
+    const WarpComm<PPR_BLOCK> comm(nullptr);
+    LaneInfo L = lane_setup(M, warp, lane, n, M.epw);
     float jq[7], jqd[6];
     load_joint_coords(L, q, qd, M.nq, M.nqd, jq, jqd);
-    BodyF s = warp_fk<JM>(M, L, jq, jqd);
+    BodyF s = warp_fk<JM>(comm, M, L, jq, jqd);
     BodyF adj = body_zero<float>();
     if (L.valid) {
         const float* a = adj_body_q + ((int64_t)L.env * M.nb + L.body) * 7;
@@ -465,12 +604,12 @@ fk_backward_kernel(DevModel M, int64_t n, const float* __restrict__ q, const flo
         adj.x = v3<float>(a[0], a[1], a[2]); adj.r = q4<float>(a[3], a[4], a[5], a[6]);
         adj.w = v3<float>(b[0], b[1], b[2]); adj.v = v3<float>(b[3], b[4], b[5]);
     }
-    warp_fk_adjoint<JM>(M, L, s, adj, jq, jqd, adj_q, adj_qd);
+    warp_fk_adjoint<JM>(comm, M, L, s, adj, jq, jqd, adj_q, adj_qd);
 }
 
 // ----------------------------------------------------------------------------------------------- rollout
 struct RolloutArgs {
-    int64_t bs, nsteps, stride, nwarps;
+    int64_t bs, nsteps, stride, nwarps, ngroups;
     float dt;
     int pstride;  // 1: per-env parameter arrays, 0: one shared copy
     const float *q_init, *qd_init, *torques, *res_f, *refs, *ke, *kd, *inv_m, *I, *inv_I;
@@ -500,8 +639,8 @@ __device__ __forceinline__ void store_wrench_row(float* base, const WrenchF& w) 
 }
 
 // forces of one substep; F = total wrench on this lane's body. Optionally exports the grf / jaf side channels.
-template <int JM, bool LIMITS, bool QOFF>
-__device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
+template <int JM, bool LIMITS, bool QOFF, class Comm>
+__device__ __forceinline__ void warp_forces(const Comm& comm, const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
                                             const M3F& Rb, F3 xc, const JointCtl<float>& ctl, const ContactMat<float>& cm0,
                                             const volatile float* st, int* clist, const float* res_f_row,
                                             float* grf_row, float* jaf_row, WrenchF& F, ContactRec& rec, float* ang) {
@@ -514,8 +653,9 @@ __device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L
     WrenchF G = F;
     if (grf_row && L.valid) store_wrench_row(grf_row, F);
     // joints: this lane is the child of its joint
-    BodyF P = shf_body(s, L.parent_lane);
-    F3 xcp = shf3(xc, L.parent_lane);
+    BodyF P;
+    F3 xcp;
+    comm.parent_state(s, xc, L.parent_slot, P, xcp);
     if (!L.has_parent) { P = body_identity<float>(); xcp = vzero<float>(); }
     F3 t, f, ap, ac;
     joint_fwd<float, JM, LIMITS, QOFF>(st_joint<QOFF>(st, L.body, L.type), ctl, M.ake, M.akd, P, xcp, L.has_parent, s,
@@ -525,46 +665,53 @@ __device__ __forceinline__ void warp_forces(const DevModel& M, const LaneInfo& L
         F.t -= t + cross(ac, f); F.f -= f;
         if (L.has_parent) { Wp.t = t + cross(ap, f); Wp.f = f; }
     }
-#pragma unroll 1
-    for (int sl = 0; sl < M.maxc; ++sl) {
-        unsigned c = (unsigned)((L.child >> (8 * sl)) & 0xffu);
-        WrenchF o = shf_wrench(Wp, c == 0xffu ? 0 : (int)c);
-        if (c != 0xffu) { F.t += o.t; F.f += o.f; }
-    }
+    comm.gather_wrench(Wp, L.child, M.maxc, F);
     if (jaf_row && L.valid) {
         WrenchF J; J.t = F.t - G.t; J.f = F.f - G.f;
         store_wrench_row(jaf_row, J);
     }
 }
 
-// Resident blocks per SM asked of ptxas: 4 x 128 threads forward (<= 128 registers), 3 adjoint (<= 168). Measured
-// on B200 (profiles/README.md): issue-slot utilisation rises with resident warps; going further costs spills.
-#ifndef PPR_FWD_MINB
-#define PPR_FWD_MINB 4
-#endif
-#ifndef PPR_BWD_MINB
-#define PPR_BWD_MINB 3
-#endif
-template <int JM, bool LIMITS, bool QOFF>
-__global__ void __launch_bounds__(PPR_BLOCK, PPR_FWD_MINB)
+// Resident blocks per SM asked of ptxas: forward <= 128 registers/thread, adjoint <= 168. Measured on B200
+// (profiles/README.md): issue-slot utilisation rises with resident warps; going further costs spills.
+#define PPR_FWD_MINB(NT) (512 / (NT))
+#define PPR_BWD_MINB(NT) (390 / (NT))
+
+// dynamic shared-memory layout (floats): [rows (adjoint only)] [static table] [params] [acc (adjoint only)] [clist] [comm]
+template <class Comm, bool ADJ> struct SmemLayout {
+    static constexpr int NT = Comm::kThreads, NW = NT / 32;
+    static constexpr int row = 0;
+    static constexpr int st = row + (ADJ ? NW * PPR_CKPT_FLOATS * 32 : 0);
+    static constexpr int par = st + PPR_NSTATIC * 32;
+    static constexpr int acc = par + PPR_NPAR * NT;
+    static constexpr int clist = acc + (ADJ ? 18 * NT : 0);
+    static constexpr int comm = clist + NW * 32 * PPR_CLIST_STRIDE;
+    static constexpr int total = comm + Comm::kExFloats;
+    static constexpr size_t bytes = (size_t)total * sizeof(float);
+};
+
+template <class Comm, int JM, bool LIMITS, bool QOFF>
+__global__ void __launch_bounds__(Comm::kThreads, PPR_FWD_MINB(Comm::kThreads))
 rollout_forward_kernel(DevModel M, RolloutArgs A) {
-    __shared__ int clist_all[PPR_WARPS * 32 * PPR_CLIST_STRIDE];
-    __shared__ float sm_st[PPR_NSTATIC * 32];  // per BLOCK: every warp stages the same per-body values
-    __shared__ float sm_par[PPR_NPAR * PPR_BLOCK];
-    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    int* clist = clist_all + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
-    volatile float* st = sm_st;
-    volatile float* par = sm_par + threadIdx.x;
-    if (warp >= A.nwarps) return;
+    constexpr int NT = Comm::kThreads;
+    typedef SmemLayout<Comm, false> SL;
+    extern __shared__ __align__(16) float smem[];
+    const Comm comm(smem + SL::comm);
+    const int64_t group = Comm::group();
+    const int64_t warp = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);  // global warp: owns checkpoint rows
+    const int lane = threadIdx.x & 31;
+    int* clist = (int*)(smem + SL::clist) + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
+    volatile float* st = smem + SL::st;
+    volatile float* par = smem + SL::par + threadIdx.x;
+    if (group >= A.ngroups) return;
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
     if (M.nc > 0) cm0 = load_mat(M, 0);
-    LaneInfo L = lane_setup(M, warp, lane, A.bs);
+    LaneInfo L = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M));
     // per-env parameters of this body / joint -> shared memory
     int64_t ebp = (int64_t)L.env * A.pstride * M.nb + L.body;
     par[0] = A.inv_m[ebp];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { par[(1 + i) * PPR_BLOCK] = A.I[ebp * 9 + i]; par[(10 + i) * PPR_BLOCK] = A.inv_I[ebp * 9 + i]; }
+    for (int i = 0; i < 9; ++i) { par[(1 + i) * NT] = A.I[ebp * 9 + i]; par[(10 + i) * NT] = A.inv_I[ebp * 9 + i]; }
     JointCtl<float> ctl;
     float ke[3], kd[3];
 #pragma unroll
@@ -580,10 +727,10 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     {
         float jq[7], jqd[6];
         load_joint_coords(L, A.q_init, A.qd_init, M.nq, M.nqd, jq, jqd);
-        s = warp_fk<JM>(M, L, jq, jqd);
-        stage_static(st, L, shf3(L.com, L.parent_lane));
+        s = warp_fk<JM>(comm, M, L, jq, jqd);
+        stage_static(st, L, comm.parent_vec(L.com, L.parent_slot));
     }
-    __syncwarp();
+    comm.sync();
 
     float* ck = A.ckpt + (warp * PPR_CKPT_FLOATS) * 32 + lane;
     const int64_t ck_step = A.nwarps * PPR_CKPT_FLOATS * 32;
@@ -607,7 +754,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         WrenchF F;
         ContactRec rec;
         float ang[3];
-        warp_forces<JM, LIMITS, QOFF>(M, L, lane, s, Rb, xc, ctl, cm0, st, clist, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
+        warp_forces<JM, LIMITS, QOFF>(comm, M, L, lane, s, Rb, xc, ctl, cm0, st, clist, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
                     (frame && A.out_grf) ? A.out_grf + frow * 6 : nullptr,
                     (frame && A.out_jaf) ? A.out_jaf + frow * 6 : nullptr, F, rec, ang);
         // checkpoint (coalesced: component-major rows of 32 lanes)
@@ -625,40 +772,40 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         if (JM != JM_REVOLUTE) { c[25 * 32] = ang[1]; c[26 * 32] = ang[2]; }
         {
             float I[9], inv_I[9];
-            par_load9(par, 1, I);
-            par_load9(par, 10, inv_I);
+            par_load9<NT>(par, 1, I);
+            par_load9<NT>(par, 10, inv_I);
             s = integrate_fwd(s, Rb, xc, com, F, par[0], I, inv_I, g, A.dt);
         }
     }
 }
 
-template <int JM, bool LIMITS, bool QOFF>
-__global__ void __launch_bounds__(PPR_BLOCK, PPR_BWD_MINB)
+template <class Comm, int JM, bool LIMITS, bool QOFF>
+__global__ void __launch_bounds__(Comm::kThreads, PPR_BWD_MINB(Comm::kThreads))
 rollout_backward_kernel(DevModel M, RolloutArgs A) {
-    __shared__ int clist_all[PPR_WARPS * 32 * PPR_CLIST_STRIDE];
-    __shared__ float sm_st[PPR_NSTATIC * 32];  // per BLOCK: every warp stages the same per-body values
-    __shared__ float sm_par[PPR_NPAR * PPR_BLOCK];
-    __shared__ float sm_acc[18 * PPR_BLOCK];
-    __shared__ __align__(16) float sm_row[PPR_WARPS * PPR_CKPT_FLOATS * 32];  // prefetched checkpoint rows, [warp][c][lane]
-    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    int* clist = clist_all + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
-    volatile float* st = sm_st;
-    volatile float* par = sm_par + threadIdx.x;
-    volatile float* acc = sm_acc + threadIdx.x;
-    volatile float* roww = sm_row + (threadIdx.x >> 5) * PPR_CKPT_FLOATS * 32;  // this warp's row buffer
+    constexpr int NT = Comm::kThreads;
+    typedef SmemLayout<Comm, true> SL;
+    extern __shared__ __align__(16) float smem[];
+    const Comm comm(smem + SL::comm);
+    const int64_t group = Comm::group();
+    const int64_t warp = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    int* clist = (int*)(smem + SL::clist) + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
+    volatile float* st = smem + SL::st;
+    volatile float* par = smem + SL::par + threadIdx.x;
+    volatile float* acc = smem + SL::acc + threadIdx.x;
+    volatile float* roww = smem + SL::row + (threadIdx.x >> 5) * PPR_CKPT_FLOATS * 32;  // this warp's row buffer
     volatile float* row = roww + (threadIdx.x & 31);
-    if (warp >= A.nwarps) return;
+    if (group >= A.ngroups) return;
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
     if (M.nc > 0) cm0 = load_mat(M, 0);
-    LaneInfo L = lane_setup(M, warp, lane, A.bs);
+    LaneInfo L = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M));
     int64_t eb = (int64_t)L.env * M.nb + L.body;
     int64_t ebp = (int64_t)L.env * A.pstride * M.nb + L.body;
     par[0] = A.inv_m[ebp];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { par[(1 + i) * PPR_BLOCK] = A.I[ebp * 9 + i]; par[(10 + i) * PPR_BLOCK] = A.inv_I[ebp * 9 + i]; }
+    for (int i = 0; i < 9; ++i) { par[(1 + i) * NT] = A.I[ebp * 9 + i]; par[(10 + i) * NT] = A.inv_I[ebp * 9 + i]; }
 #pragma unroll
-    for (int i = 0; i < 18; ++i) acc[i * PPR_BLOCK] = 0.f;
+    for (int i = 0; i < 18; ++i) acc[i * NT] = 0.f;
     JointCtl<float> ctl;
     float ke[3], kd[3];
     const bool jon = L.type != JT_FREE;
@@ -672,8 +819,8 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     }
     F3 g = v3<float>(M.g[0], M.g[1], M.g[2]);
     // com of the parent body (to fold the parent's world-COM adjoint into its pose adjoint in the child lane)
-    stage_static(st, L, shf3(L.com, L.parent_lane));
-    __syncwarp();
+    stage_static(st, L, comm.parent_vec(L.com, L.parent_slot));
+    comm.sync();
 
     float a_inv_m = 0.f, a_ke[3] = {0, 0, 0}, a_kd[3] = {0, 0, 0};
 
@@ -746,8 +893,8 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         WrenchF adjF;
         {
             float I[9], inv_I[9];
-            par_load9(par, 1, I);
-            par_load9(par, 10, inv_I);
+            par_load9<NT>(par, 1, I);
+            par_load9<NT>(par, 10, inv_I);
             F3 ga, gb, gc, gd;
             integrate_adj_core(s, Rb, xc, com, F, par[0], I, inv_I, g, A.dt, adjN, adjS, G, adj_xc, adjF, a_inv_m, ga,
                                gb, gc, gd);
@@ -757,14 +904,15 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
             for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    acc[(3 * i + j) * PPR_BLOCK] += av[i] * bv[j];
-                    acc[(9 + 3 * i + j) * PPR_BLOCK] += cv[i] * dv[j];
+                    acc[(3 * i + j) * NT] += av[i] * bv[j];
+                    acc[(9 + 3 * i + j) * NT] += cv[i] * dv[j];
                 }
         }
         // K4^T (this lane = child of its joint)
-        BodyF P = shf_body(s, L.parent_lane);
-        F3 xcp = shf3(xc, L.parent_lane);
-        WrenchF adjFp = shf_wrench(adjF, L.parent_lane);
+        BodyF P;
+        F3 xcp;
+        WrenchF adjFp;
+        comm.parent_state_w(s, xc, adjF, L.parent_slot, P, xcp, adjFp);
         if (!L.has_parent) { P = body_identity<float>(); xcp = vzero<float>(); adjFp = wrench_zero<float>(); }
         BodyF adjP = body_zero<float>();
         F3 adj_xcp = vzero<float>();
@@ -775,7 +923,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         adjP.x += adj_xcp;
         adjP.r += qrot_adj_q(P.r, st_vec3(st, ST_CPAR, L.body), adj_xcp);
         if (!L.has_parent) adjP = body_zero<float>();
-        gather_children_body(M, L, adjP, adjS);
+        comm.gather_body(adjP, L.child, M.maxc, adjS);
         if (L.valid) {
             int64_t row = (tp * A.bs + L.env) * M.nqd + L.qds;
 #pragma unroll
@@ -805,15 +953,16 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     // K1^T: state 0 = eval_fk(q_init, qd_init), recomputed
     {
         float jq[7], jqd[6];
-        LaneInfo L2 = lane_setup(M, warp, lane, A.bs);  // re-derived: the static joint data lived in smem meanwhile
+        comm.sync();
+        LaneInfo L2 = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M));  // re-derived (was in smem)
         load_joint_coords(L2, A.q_init, A.qd_init, M.nq, M.nqd, jq, jqd);
-        BodyF s0 = warp_fk<JM>(M, L2, jq, jqd);
-        warp_fk_adjoint<JM>(M, L2, s0, adjN, jq, jqd, A.adj_q_init, A.adj_qd_init);
+        BodyF s0 = warp_fk<JM>(comm, M, L2, jq, jqd);
+        warp_fk_adjoint<JM>(comm, M, L2, s0, adjN, jq, jqd, A.adj_q_init, A.adj_qd_init);
     }
     if (L.valid) {
         A.adj_inv_m[eb] = nan0(a_inv_m);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) { A.adj_I[eb * 9 + i] = nan0(acc[i * PPR_BLOCK]); A.adj_inv_I[eb * 9 + i] = nan0(acc[(9 + i) * PPR_BLOCK]); }
+        for (int i = 0; i < 9; ++i) { A.adj_I[eb * 9 + i] = nan0(acc[i * NT]); A.adj_inv_I[eb * 9 + i] = nan0(acc[(9 + i) * NT]); }
         int64_t d = (int64_t)L.env * M.nqd + L.qds;
 #pragma unroll
         for (int k = 0; k < 3; ++k) if (jon && k < L.ndof) { A.adj_ke[d + k] = nan0(a_ke[k]); A.adj_kd[d + k] = nan0(a_kd[k]); }
@@ -950,6 +1099,18 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
         if (!any_cmp) m->variant = 0;
         else if (!any_rev) m->variant = 1;
     }
+    // env packing: lanes doing useful work per warp-packed warp vs per block-packed block
+    {
+        double best = (double)((32 / nb) * nb) / 32.0;
+        m->comm = 0;
+        for (int c = 1; c < 3; ++c) {
+            int nt = kCommThreads[c];
+            double u = (double)((nt / nb) * nb) / nt;
+            if (u > best * 1.12) { best = u; m->comm = c; }  // the barriers must buy at least ~12 % more useful lanes
+        }
+        const char* ov = getenv("PPR_COMM");
+        if (ov && ov[0] >= '0' && ov[0] <= '2') m->comm = ov[0] - '0';
+    }
     m->xpj_offset = o_xpj;
     m->h_xpj.assign(D->joint_X_p, D->joint_X_p + nb * 7);
     m->magic = PPR_MAGIC;
@@ -984,9 +1145,71 @@ extern "C" int ppr_model_set_gravity(ppr_model_t m, const float g[3]) {
     m->d.g[0] = g[0]; m->d.g[1] = g[1]; m->d.g[2] = g[2];
     return 0;
 }
-extern "C" int ppr_model_envs_per_warp(ppr_model_t m) { return check(m) ? m->d.epw : PPR_E_HANDLE; }
+extern "C" int ppr_model_envs_per_group(ppr_model_t m) {
+    if (!check(m)) return PPR_E_HANDLE;
+    return m->comm == 0 ? m->d.epw : kCommThreads[m->comm] / m->d.nb;
+}
+extern "C" int ppr_model_group_threads(ppr_model_t m) {
+    if (!check(m)) return PPR_E_HANDLE;
+    return m->comm == 0 ? 32 : kCommThreads[m->comm];
+}
 
 static inline int64_t nwarps_for(const DevModel& d, int64_t n) { return (n + d.epw - 1) / d.epw; }
+// rollout kernels: groups (warps or blocks) and warps (each owns one checkpoint row per substep)
+static inline void rollout_geometry(const ppr_model* m, int64_t bs, int64_t& ngroups, int64_t& nwarps, unsigned& grid) {
+    const int nt = kCommThreads[m->comm];
+    if (m->comm == 0) {
+        ngroups = nwarps_for(m->d, bs);
+        grid = (unsigned)((ngroups * 32 + nt - 1) / nt);
+        nwarps = ngroups;
+    } else {
+        int epb = nt / m->d.nb;
+        ngroups = (bs + epb - 1) / epb;
+        grid = (unsigned)ngroups;
+        nwarps = ngroups * (nt / 32);
+    }
+}
+template <class K> static cudaError_t launch_rollout(K kernel, size_t smem, unsigned grid, int nt, cudaStream_t st,
+                                                     const DevModel& d, const RolloutArgs& A) {
+    // opt in to > 48 kB of dynamic shared memory once per kernel instantiation (all instantiations share this
+    // function template because they have the same signature, hence the small pointer table)
+    static std::atomic<const void*> done[64];
+    bool found = false;
+    for (int i = 0; i < 64 && !found; ++i) {
+        const void* p = done[i].load(std::memory_order_acquire);
+        if (p == (const void*)kernel) found = true;
+        else if (p == nullptr) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            done[i].store((const void*)kernel, std::memory_order_release);
+            found = true;
+        }
+    }
+    kernel<<<grid, nt, smem, st>>>(d, A);
+    return cudaGetLastError();
+}
+#define PPR_LAUNCH_ROLLOUT(KERNEL, ADJ)                                                                              \
+    do {                                                                                                             \
+        cudaError_t e_;                                                                                              \
+        if (m->comm == 0) {                                                                                          \
+            typedef WarpComm<128> C_;                                                                                \
+            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, m->d, A); \
+            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, m->d, A); \
+            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, m->d, A); \
+        } else if (m->comm == 1) {                                                                                   \
+            typedef BlockComm<96> C_;                                                                                \
+            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, m->d, A); \
+            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, m->d, A); \
+            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, m->d, A); \
+        } else {                                                                                                     \
+            typedef BlockComm<160> C_;                                                                               \
+            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, m->d, A); \
+            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, m->d, A); \
+            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, m->d, A); \
+        }                                                                                                            \
+        g_launches++;                                                                                                \
+        return (int)e_;                                                                                              \
+    } while (0)
 static inline unsigned grid_for(int64_t nwarps) { return (unsigned)((nwarps * 32 + PPR_BLOCK - 1) / PPR_BLOCK); }
 
 extern "C" int ppr_fk_forward(ppr_model_t m, int64_t n, const float* q, const float* qd, float* bq, float* bqd,
@@ -1019,7 +1242,9 @@ extern "C" int ppr_fk_backward(ppr_model_t m, int64_t n, const float* q, const f
 
 extern "C" size_t ppr_rollout_workspace_bytes(ppr_model_t m, int64_t bs, int64_t nsteps) {
     if (!check(m) || bs <= 0 || nsteps <= 0) return 0;
-    return (size_t)nwarps_for(m->d, bs) * (size_t)nsteps * PPR_CKPT_FLOATS * 32 * sizeof(float);
+    int64_t ngroups, nwarps; unsigned grid;
+    rollout_geometry(m, bs, ngroups, nwarps, grid);
+    return (size_t)nwarps * (size_t)nsteps * PPR_CKPT_FLOATS * 32 * sizeof(float);
 }
 
 extern "C" int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t stride, float dt,
@@ -1035,18 +1260,15 @@ extern "C" int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, in
     if (ws_bytes < ppr_rollout_workspace_bytes(m, bs, nsteps)) return PPR_E_WORKSPACE;
     RolloutArgs A;
     memset(&A, 0, sizeof(A));
-    A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.nwarps = nwarps_for(m->d, bs); A.dt = dt;
+    unsigned grid;
+    rollout_geometry(m, bs, A.ngroups, A.nwarps, grid);
+    A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.dt = dt;
     A.pstride = shared_params ? 0 : 1;
     A.q_init = q_init; A.qd_init = qd_init; A.torques = torques; A.res_f = res_f; A.refs = refs; A.ke = ke; A.kd = kd;
     A.inv_m = inv_m; A.I = I; A.inv_I = inv_I;
     A.out_pos = out_pos; A.out_vel = out_vel; A.out_grf = out_grf; A.out_jaf = out_jaf; A.ckpt = (float*)ws;
-    dim3 grid(grid_for(A.nwarps));
     cudaStream_t st = (cudaStream_t)stream;
-    if (m->variant == 0) rollout_forward_kernel<JM_REVOLUTE, false, false><<<grid, PPR_BLOCK, 0, st>>>(m->d, A);
-    else if (m->variant == 1) rollout_forward_kernel<JM_COMPOUND, false, false><<<grid, PPR_BLOCK, 0, st>>>(m->d, A);
-    else rollout_forward_kernel<JM_ALL, true, true><<<grid, PPR_BLOCK, 0, st>>>(m->d, A);
-    g_launches++;
-    return (int)cudaGetLastError();
+    PPR_LAUNCH_ROLLOUT(rollout_forward_kernel, false);
 }
 
 extern "C" int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t stride, float dt,
@@ -1065,18 +1287,15 @@ extern "C" int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, i
     if (ws_bytes < ppr_rollout_workspace_bytes(m, bs, nsteps)) return PPR_E_WORKSPACE;
     RolloutArgs A;
     memset(&A, 0, sizeof(A));
-    A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.nwarps = nwarps_for(m->d, bs); A.dt = dt;
+    unsigned grid;
+    rollout_geometry(m, bs, A.ngroups, A.nwarps, grid);
+    A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.dt = dt;
     A.pstride = shared_params ? 0 : 1;
     A.q_init = q_init; A.qd_init = qd_init; A.torques = torques; A.res_f = res_f; A.refs = refs; A.ke = ke; A.kd = kd;
     A.inv_m = inv_m; A.I = I; A.inv_I = inv_I; A.ckpt = (float*)ws;
     A.adj_pos = adj_pos; A.adj_vel = adj_vel; A.adj_q_init = adj_q_init; A.adj_qd_init = adj_qd_init;
     A.adj_torques = adj_torques; A.adj_res_f = adj_res_f; A.adj_refs = adj_refs; A.adj_ke = adj_ke; A.adj_kd = adj_kd;
     A.adj_inv_m = adj_inv_m; A.adj_I = adj_I; A.adj_inv_I = adj_inv_I;
-    dim3 grid(grid_for(A.nwarps));
     cudaStream_t st = (cudaStream_t)stream;
-    if (m->variant == 0) rollout_backward_kernel<JM_REVOLUTE, false, false><<<grid, PPR_BLOCK, 0, st>>>(m->d, A);
-    else if (m->variant == 1) rollout_backward_kernel<JM_COMPOUND, false, false><<<grid, PPR_BLOCK, 0, st>>>(m->d, A);
-    else rollout_backward_kernel<JM_ALL, true, true><<<grid, PPR_BLOCK, 0, st>>>(m->d, A);
-    g_launches++;
-    return (int)cudaGetLastError();
+    PPR_LAUNCH_ROLLOUT(rollout_backward_kernel, true);
 }

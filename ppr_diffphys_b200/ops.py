@@ -117,8 +117,9 @@ class SimEnv:
         _lib.check(self._lib.ppr_model_set_gravity(self._h, arr), "ppr_model_set_gravity")
 
     @property
-    def envs_per_warp(self):
-        return int(self._lib.ppr_model_envs_per_warp(self._h))
+    def packing(self):
+        """(threads per group, environments per group): a group is a warp or a thread block."""
+        return int(self._lib.ppr_model_group_threads(self._h)), int(self._lib.ppr_model_envs_per_group(self._h))
 
     def __del__(self):
         try:

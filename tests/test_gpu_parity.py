@@ -350,7 +350,9 @@ def test_c_abi_error_codes():
     args = [p] * 2 + [n, n] + [p] * 6 + [p, p, n, n]
     assert lib.ppr_rollout_forward(h, 2, 65, 32, C.c_float(5e-4), 0, *args, p, C.c_size_t(16), n) == -4  # workspace
     assert lib.ppr_rollout_forward(h, 0, 65, 32, C.c_float(5e-4), 0, *args, p, C.c_size_t(16), n) == 0   # empty batch
-    assert lib.ppr_rollout_workspace_bytes(h, 2, 65) == 1 * 65 * 28 * 32 * 4
+    threads, epg = env.packing
+    assert threads in (32, 96, 160) and epg == threads // env.nb
+    assert lib.ppr_rollout_workspace_bytes(h, 2, 65) == -(-2 // epg) * (threads // 32) * 65 * 28 * 32 * 4
     before = _lib.launch_count()
     env.fk(torch.zeros(3, env.nq, device="cuda"), torch.zeros(3, env.nqd, device="cuda"))
     assert _lib.launch_count() == before + 1
