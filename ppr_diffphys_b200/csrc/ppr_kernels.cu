@@ -115,6 +115,26 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Split-phase CTA barriers (mbarrier): a thread ARRIVES as soon as it has published its values and only WAITS when
+// it needs its partner's, so independent work (the contact pass) between the two hides the skew between the warps
+// of a block instead of stalling on a __syncthreads.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 // ----------------------------------------------------------------------------------------------- tree exchange
 // Collectives over the articulation tree, executed by EVERY thread of the group (warp or block):
 //   parent_*  : each thread obtains values held by the thread of its parent body
@@ -131,11 +151,17 @@ template <int NT> struct WarpComm {
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     __device__ __forceinline__ BodyF parent_body(const BodyF& s, int ps) const { return shf_body(s, ps); }
     __device__ __forceinline__ F3 parent_vec(F3 v, int ps) const { return shf3(v, ps); }
-    __device__ __forceinline__ void parent_state(const BodyF& s, F3 xc, int ps, BodyF& P, F3& xcp) const {
+    __device__ __forceinline__ void init() {}
+    // split-phase API: post_* publishes (no-op here), get_* / gather_* obtains the partner's values
+    __device__ __forceinline__ void post_state(const BodyF&, F3) {}
+    __device__ __forceinline__ void post_state_w(const BodyF&, F3, const WrenchF&) {}
+    __device__ __forceinline__ void post_wrench(const WrenchF&) {}
+    __device__ __forceinline__ void post_body(const BodyF&) {}
+    __device__ __forceinline__ void get_parent_state(const BodyF& s, F3 xc, int ps, BodyF& P, F3& xcp) {
         P = shf_body(s, ps); xcp = shf3(xc, ps);
     }
-    __device__ __forceinline__ void parent_state_w(const BodyF& s, F3 xc, const WrenchF& w, int ps, BodyF& P, F3& xcp,
-                                                   WrenchF& wp) const {
+    __device__ __forceinline__ void get_parent_state_w(const BodyF& s, F3 xc, const WrenchF& w, int ps, BodyF& P, F3& xcp,
+                                                       WrenchF& wp) {
         P = shf_body(s, ps); xcp = shf3(xc, ps); wp = shf_wrench(w, ps);
     }
     __device__ __forceinline__ void gather_wrench(const WrenchF& mine, unsigned long long child, int maxc,
@@ -155,6 +181,10 @@ template <int NT> struct WarpComm {
             if (c != 0xffu) body_acc(acc, o);
         }
     }
+    __device__ __forceinline__ void gather_body_sync(const BodyF& mine, unsigned long long child, int maxc,
+                                                     BodyF& acc) const {
+        gather_body(mine, child, maxc, acc);
+    }
 };
 
 // Block-wide variant: values are published in shared memory ([component][thread], conflict-free), one
@@ -165,10 +195,17 @@ template <int NT> struct WarpComm {
 template <int NT> struct BlockComm {
     static constexpr int kThreads = NT;
     static constexpr bool kBlock = true;
-    static constexpr int kExFloats = (22 + 13) * NT;
+    static constexpr int kExFloats = (22 + 13) * NT + 4;  // + two 8-byte mbarriers
     float* ex;   // [22][NT]
     float* msg;  // [13][NT]
-    __device__ __forceinline__ explicit BlockComm(float* sm) : ex(sm), msg(sm + 22 * NT) {}
+    unsigned long long* bar;  // [0]: `ex` published, [1]: `msg` published
+    unsigned phA, phB;
+    __device__ __forceinline__ explicit BlockComm(float* sm)
+        : ex(sm), msg(sm + 22 * NT), bar((unsigned long long*)(sm + 35 * NT)), phA(0), phB(0) {}
+    __device__ __forceinline__ void init() {
+        if (threadIdx.x == 0) { mbar_init(bar, NT); mbar_init(bar + 1, NT); }
+        __syncthreads();
+    }
     static __device__ __forceinline__ int64_t group() { return blockIdx.x; }
     static __device__ __forceinline__ int slot() { return threadIdx.x; }
     static __device__ __forceinline__ int envs_per_group(const DevModel& M) { return NT / M.nb; }
@@ -203,33 +240,48 @@ template <int NT> struct BlockComm {
         __syncthreads();
         return o;
     }
-    __device__ __forceinline__ void parent_state(const BodyF& s, F3 xc, int ps, BodyF& P, F3& xcp) const {
+    // ---- split phase: in the substep loops a post_state* / get_parent_state* pair (area `ex`, barrier A) always
+    // alternates with a post_* / gather_* pair (area `msg`, barrier B); a thread can only pass wait(B) of substep t
+    // after every thread has arrived at B, i.e. after it finished reading `ex` of substep t, and vice versa.
+    __device__ __forceinline__ void post_state(const BodyF& s, F3 xc) {
         const int t = threadIdx.x;
         put_body(ex, s);
         ex[13 * NT + t] = xc.x; ex[14 * NT + t] = xc.y; ex[15 * NT + t] = xc.z;
-        __syncthreads();
-        P = get_body(ex, ps);
-        xcp = v3<float>(ex[13 * NT + ps], ex[14 * NT + ps], ex[15 * NT + ps]);
+        mbar_arrive(bar);
     }
-    __device__ __forceinline__ void parent_state_w(const BodyF& s, F3 xc, const WrenchF& w, int ps, BodyF& P, F3& xcp,
-                                                   WrenchF& wp) const {
+    __device__ __forceinline__ void post_state_w(const BodyF& s, F3 xc, const WrenchF& w) {
         const int t = threadIdx.x;
         put_body(ex, s);
         ex[13 * NT + t] = xc.x; ex[14 * NT + t] = xc.y; ex[15 * NT + t] = xc.z;
         ex[16 * NT + t] = w.t.x; ex[17 * NT + t] = w.t.y; ex[18 * NT + t] = w.t.z;
         ex[19 * NT + t] = w.f.x; ex[20 * NT + t] = w.f.y; ex[21 * NT + t] = w.f.z;
-        __syncthreads();
+        mbar_arrive(bar);
+    }
+    __device__ __forceinline__ void get_parent_state(const BodyF&, F3, int ps, BodyF& P, F3& xcp) {
+        mbar_wait(bar, phA); phA ^= 1u;
+        P = get_body(ex, ps);
+        xcp = v3<float>(ex[13 * NT + ps], ex[14 * NT + ps], ex[15 * NT + ps]);
+    }
+    __device__ __forceinline__ void get_parent_state_w(const BodyF&, F3, const WrenchF&, int ps, BodyF& P, F3& xcp,
+                                                       WrenchF& wp) {
+        mbar_wait(bar, phA); phA ^= 1u;
         P = get_body(ex, ps);
         xcp = v3<float>(ex[13 * NT + ps], ex[14 * NT + ps], ex[15 * NT + ps]);
         wp.t = v3<float>(ex[16 * NT + ps], ex[17 * NT + ps], ex[18 * NT + ps]);
         wp.f = v3<float>(ex[19 * NT + ps], ex[20 * NT + ps], ex[21 * NT + ps]);
     }
-    __device__ __forceinline__ void gather_wrench(const WrenchF& mine, unsigned long long child, int maxc,
-                                                  WrenchF& acc) const {
+    __device__ __forceinline__ void post_wrench(const WrenchF& mine) {
         const int t = threadIdx.x;
         msg[0 * NT + t] = mine.t.x; msg[1 * NT + t] = mine.t.y; msg[2 * NT + t] = mine.t.z;
         msg[3 * NT + t] = mine.f.x; msg[4 * NT + t] = mine.f.y; msg[5 * NT + t] = mine.f.z;
-        __syncthreads();
+        mbar_arrive(bar + 1);
+    }
+    __device__ __forceinline__ void post_body(const BodyF& mine) {
+        put_body(msg, mine);
+        mbar_arrive(bar + 1);
+    }
+    __device__ __forceinline__ void gather_wrench(const WrenchF&, unsigned long long child, int maxc, WrenchF& acc) {
+        mbar_wait(bar + 1, phB); phB ^= 1u;
 #pragma unroll 1
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
@@ -239,7 +291,17 @@ template <int NT> struct BlockComm {
             }
         }
     }
-    __device__ __forceinline__ void gather_body(const BodyF& mine, unsigned long long child, int maxc, BodyF& acc) const {
+    __device__ __forceinline__ void gather_body(const BodyF&, unsigned long long child, int maxc, BodyF& acc) {
+        mbar_wait(bar + 1, phB); phB ^= 1u;
+#pragma unroll 1
+        for (int sl = 0; sl < maxc; ++sl) {
+            unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
+            if (c != 0xffu) body_acc(acc, get_body(msg, (int)c));
+        }
+    }
+    // plain-barrier variant for the FK adjoint (outside the substep loop)
+    __device__ __forceinline__ void gather_body_sync(const BodyF& mine, unsigned long long child, int maxc,
+                                                     BodyF& acc) const {
         put_body(msg, mine);
         __syncthreads();
 #pragma unroll 1
@@ -247,6 +309,7 @@ template <int NT> struct BlockComm {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
             if (c != 0xffu) body_acc(acc, get_body(msg, (int)c));
         }
+        __syncthreads();
     }
 };
 
@@ -572,8 +635,7 @@ __device__ __forceinline__ void warp_fk_adjoint(const Comm& comm, const DevModel
         if (!L.has_parent) P = body_identity<float>();
         BodyF adjP = body_zero<float>();
         if (L.depth == d) fk_joint_adj<float, JM>(L.js, L.com, P, jq, jqd, adj, adjP, ajq, ajqd);
-        comm.gather_body(adjP, L.child, M.maxc, adj);
-        comm.sync();
+        comm.gather_body_sync(adjP, L.child, M.maxc, adj);
     }
     if (L.valid) {
         int ncoord = L.type == JT_FREE ? 7 : L.ndof;
@@ -640,10 +702,11 @@ __device__ __forceinline__ void store_wrench_row(float* base, const WrenchF& w) 
 
 // forces of one substep; F = total wrench on this lane's body. Optionally exports the grf / jaf side channels.
 template <int JM, bool LIMITS, bool QOFF, class Comm>
-__device__ __forceinline__ void warp_forces(const Comm& comm, const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
+__device__ __forceinline__ void warp_forces(Comm& comm, const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
                                             const M3F& Rb, F3 xc, const JointCtl<float>& ctl, const ContactMat<float>& cm0,
                                             const volatile float* st, int* clist, const float* res_f_row,
                                             float* grf_row, float* jaf_row, WrenchF& F, ContactRec& rec, float* ang) {
+    comm.post_state(s, xc);   // published before the (long, warp-dependent) contact pass, awaited after it
     F = wrench_zero<float>();
     if (res_f_row && L.valid) {
         F.t = v3<float>(res_f_row[0], res_f_row[1], res_f_row[2]);
@@ -655,7 +718,7 @@ __device__ __forceinline__ void warp_forces(const Comm& comm, const DevModel& M,
     // joints: this lane is the child of its joint
     BodyF P;
     F3 xcp;
-    comm.parent_state(s, xc, L.parent_slot, P, xcp);
+    comm.get_parent_state(s, xc, L.parent_slot, P, xcp);
     if (!L.has_parent) { P = body_identity<float>(); xcp = vzero<float>(); }
     F3 t, f, ap, ac;
     joint_fwd<float, JM, LIMITS, QOFF>(st_joint<QOFF>(st, L.body, L.type), ctl, M.ake, M.akd, P, xcp, L.has_parent, s,
@@ -665,6 +728,7 @@ __device__ __forceinline__ void warp_forces(const Comm& comm, const DevModel& M,
         F.t -= t + cross(ac, f); F.f -= f;
         if (L.has_parent) { Wp.t = t + cross(ap, f); Wp.f = f; }
     }
+    comm.post_wrench(Wp);
     comm.gather_wrench(Wp, L.child, M.maxc, F);
     if (jaf_row && L.valid) {
         WrenchF J; J.t = F.t - G.t; J.f = F.f - G.f;
@@ -696,7 +760,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     constexpr int NT = Comm::kThreads;
     typedef SmemLayout<Comm, false> SL;
     extern __shared__ __align__(16) float smem[];
-    const Comm comm(smem + SL::comm);
+    Comm comm(smem + SL::comm);
     const int64_t group = Comm::group();
     const int64_t warp = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);  // global warp: owns checkpoint rows
     const int lane = threadIdx.x & 31;
@@ -704,6 +768,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     volatile float* st = smem + SL::st;
     volatile float* par = smem + SL::par + threadIdx.x;
     if (group >= A.ngroups) return;
+    comm.init();
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
     if (M.nc > 0) cm0 = load_mat(M, 0);
     LaneInfo L = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M));
@@ -785,7 +850,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     constexpr int NT = Comm::kThreads;
     typedef SmemLayout<Comm, true> SL;
     extern __shared__ __align__(16) float smem[];
-    const Comm comm(smem + SL::comm);
+    Comm comm(smem + SL::comm);
     const int64_t group = Comm::group();
     const int64_t warp = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -796,6 +861,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     volatile float* roww = smem + SL::row + (threadIdx.x >> 5) * PPR_CKPT_FLOATS * 32;  // this warp's row buffer
     volatile float* row = roww + (threadIdx.x & 31);
     if (group >= A.ngroups) return;
+    comm.init();
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
     if (M.nc > 0) cm0 = load_mat(M, 0);
     LaneInfo L = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M));
@@ -908,11 +974,20 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
                     acc[(9 + 3 * i + j) * NT] += cv[i] * dv[j];
                 }
         }
+        comm.post_state_w(s, xc, adjF);   // published before the contact replay, awaited after it
+        // K3^T (needs only this body's adjF)
+        warp_contacts_adj(M, L, lane, s, Rb, xc, cm0, st, clist, rec, adjF, adjS, G, adj_xc);
+        // K2^T
+        if (A.adj_res_f && L.valid) {
+            float* r = A.adj_res_f + ((tp * A.bs + L.env) * M.nb + L.body) * 6;
+            r[0] = nan0(adjF.t.x); r[1] = nan0(adjF.t.y); r[2] = nan0(adjF.t.z);
+            r[3] = nan0(adjF.f.x); r[4] = nan0(adjF.f.y); r[5] = nan0(adjF.f.z);
+        }
         // K4^T (this lane = child of its joint)
         BodyF P;
         F3 xcp;
         WrenchF adjFp;
-        comm.parent_state_w(s, xc, adjF, L.parent_slot, P, xcp, adjFp);
+        comm.get_parent_state_w(s, xc, adjF, L.parent_slot, P, xcp, adjFp);
         if (!L.has_parent) { P = body_identity<float>(); xcp = vzero<float>(); adjFp = wrench_zero<float>(); }
         BodyF adjP = body_zero<float>();
         F3 adj_xcp = vzero<float>();
@@ -923,7 +998,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         adjP.x += adj_xcp;
         adjP.r += qrot_adj_q(P.r, st_vec3(st, ST_CPAR, L.body), adj_xcp);
         if (!L.has_parent) adjP = body_zero<float>();
-        comm.gather_body(adjP, L.child, M.maxc, adjS);
+        comm.post_body(adjP);
         if (L.valid) {
             int64_t row = (tp * A.bs + L.env) * M.nqd + L.qds;
 #pragma unroll
@@ -936,14 +1011,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
                 if (A.adj_torques) A.adj_torques[row + k] = 0.f;
             }
         }
-        // K3^T
-        warp_contacts_adj(M, L, lane, s, Rb, xc, cm0, st, clist, rec, adjF, adjS, G, adj_xc);
-        // K2^T
-        if (A.adj_res_f && L.valid) {
-            float* r = A.adj_res_f + ((tp * A.bs + L.env) * M.nb + L.body) * 6;
-            r[0] = nan0(adjF.t.x); r[1] = nan0(adjF.t.y); r[2] = nan0(adjF.t.z);
-            r[3] = nan0(adjF.f.x); r[4] = nan0(adjF.f.y); r[5] = nan0(adjF.f.z);
-        }
+        comm.gather_body(adjP, L.child, M.maxc, adjS);
         // world COM -> pose
         adjS.x += adj_xc;
         m3_acc(G, adj_xc, com);
