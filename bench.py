@@ -172,7 +172,7 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     from ppr_diffphys_b200 import ForwardWarp, SimEnv, _lib, load_robot
-    from ppr_diffphys_b200.synth import make_batch, mass_chain, shared_param_chain
+    from ppr_diffphys_b200.synth import make_batch, shared_param_chain
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -260,7 +260,8 @@ def run_gpu_arm(args):
     ke = p_ke.detach()[None].expand(bs, nqd).reshape(-1).contiguous()
     kd = p_kd.detach()[None].expand(bs, nqd).reshape(-1).contiguous()
     mass = p_mass.detach()[None].expand(bs, nb).reshape(-1).contiguous()
-    inv_m, I, inv_I = mass_chain(mass, nI)
+    inv_m, I = 1.0 / mass, (nI[None].expand(bs, nb, 3, 3).reshape(-1, 3, 3) * mass[:, None, None]).contiguous()
+    inv_I = (nI_inv[None].expand(bs, nb, 3, 3).reshape(-1, 3, 3) * inv_m[:, None, None]).contiguous()
     ws = None
     evs = []
     for i in range(max(args.steps, 5) + 1):

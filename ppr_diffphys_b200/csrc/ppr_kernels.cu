@@ -3,15 +3,16 @@
 //
 // Mapping: one THREAD per rigid body. Environments are packed either per WARP (floor(32/nb) envs per warp, tree
 // exchange by warp shuffles) or per BLOCK (floor(NT/nb) envs per block of NT threads, tree exchange through shared
-// memory + __syncthreads) -- whichever wastes fewer lanes: human has 19 bodies, i.e. 59 % lane use per warp but
-// 99 % with 5 envs in a 96-thread block. The two are the `Comm` policy of the kernels below.
+// memory + split-phase mbarriers) -- whichever wastes fewer lanes: human has 19 bodies, i.e. 59 % lane use per warp
+// but 99 % with 5 envs in a 96-thread block. The two are the `Comm` policy of the kernels below.
 // The body state (13 floats) lives in registers for the whole rollout; parent/child exchange of states and
-// wrenches is done with warp shuffles on the static articulation tree (no shared memory, no atomics ->
-// deterministic, unlike the reference's atomic_add/sub at integrator_euler.py:179,449,451).  The time loop is
-// inside the kernel: one launch per rollout instead of the reference's 4 launches + 1 memset + 2 clones per
-// substep (dp_model.py:1209-1228).  Per substep the forward kernel streams the state and the total body wrench
-// (19 floats / body) to an HBM checkpoint buffer laid out [t][warp][component][lane] (128-byte coalesced rows);
-// the backward kernel streams it back in reverse and recomputes every other intermediate.
+// wrenches follows the static articulation tree with ordered reads (no atomics -> deterministic, unlike the
+// reference's atomic_add/sub at integrator_euler.py:179,449,451).  The time loop is inside the kernel: one launch
+// per rollout instead of the reference's 4 launches + 1 memset + 2 clones per substep (dp_model.py:1209-1228).
+// Per substep the forward kernel streams the state, the total body wrench, the active-contact record and the joint
+// angles (28 floats / body) to an HBM checkpoint buffer laid out [t][warp][component][lane] (128-byte coalesced
+// rows); the adjoint kernel streams it back in reverse (cp.async, one substep ahead) and recomputes every other
+// intermediate.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -36,8 +37,7 @@ typedef M3<float> M3F;
 #define PPR_CKPT_FLOATS 28  // body_q 7 + body_qd 6 + total wrench 6 + active-contact record 5 (count, 8 x u16) +
                            // joint angles 3 + pad 1 (rows stay a multiple of 32 x 16 bytes)
 #define PPR_REC_MAX 8
-#define PPR_BLOCK 128
-#define PPR_WARPS (PPR_BLOCK / 32)
+#define PPR_BLOCK 128  // FK kernels (warp layout)
 #define PPR_CLIST_CAP 16  // penetrating points listed per body before falling back to the cooperative path
 #define PPR_CLIST_STRIDE (PPR_CLIST_CAP + 1)
 #define FULL 0xffffffffu
@@ -316,8 +316,8 @@ template <int NT> struct BlockComm {
 // Shared-memory residency of everything that is constant over the time loop, so that it does not occupy
 // registers for the whole rollout (the kernels are occupancy/latency bound):
 //   static per-BODY table  sm_st[PPR_NSTATIC][32]   (indexed by body; lanes of different envs broadcast-read)
-//   per-LANE parameters    sm_par[PPR_NPAR][PPR_BLOCK]  inv_m, I[9], inv_I[9]
-//   per-LANE accumulators  sm_acc[18][PPR_BLOCK]        adj_I, adj_inv_I        (adjoint kernel only)
+//   per-THREAD parameters   par[PPR_NPAR][NT]   inv_m, I[9], inv_I[9]
+//   per-THREAD accumulators acc[18][NT]         adj_I, adj_inv_I        (adjoint kernel only)
 // Reads go through volatile pointers so that ptxas re-issues the (29-cycle) LDS at the point of use instead of
 // hoisting the values back into loop-long registers.
 #define PPR_NSTATIC 28  // xpj 3, qpj 4, axis 3, com 3, parent com 3, aabb 7, qoff 4, pad 1

@@ -53,16 +53,6 @@ def make_batch(env, bs, nsteps, seed=0, clearance=1e-3, ang=0.2, qd_std=0.1, ref
     return host
 
 
-def mass_chain(body_mass, norm_body_inertia):
-    """body_mass [bs*nb] -> inv_mass, inertia, inv_inertia exactly like dp_model.py:725-730 (differentiable)."""
-    nI = norm_body_inertia
-    bs = body_mass.numel() // nI.shape[0]
-    inv_m = 1.0 / body_mass
-    I = nI[None].repeat(bs, 1, 1, 1).view(-1, 3, 3) * body_mass[..., None, None]
-    inv_I = torch.linalg.inv(I).contiguous()
-    return inv_m, I, inv_I
-
-
 def shared_param_chain(target_ke, target_kd, body_mass, norm_body_inertia, bs):
     """Shared parameters [nqd], [nqd], [nb] -> the per-env replicated tensors ForwardWarp.apply expects
     (dp_model.py:723-730).  Same values as the reference's chain, but the 3x3 inverse is taken on the nb shared
