@@ -795,7 +795,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         s = warp_fk<JM>(comm, M, L, jq, jqd);
         stage_static(st, L, comm.parent_vec(L.com, L.parent_slot));
     }
-    comm.sync();
+    __syncthreads();  // the static table is per block (all warps stage identical values)
 
     float* ck = A.ckpt + (warp * PPR_CKPT_FLOATS) * 32 + lane;
     const int64_t ck_step = A.nwarps * PPR_CKPT_FLOATS * 32;
@@ -833,8 +833,8 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         c[19 * 32] = __uint_as_float(rec.cnt);
         c[20 * 32] = __uint_as_float((unsigned)rec.lo); c[21 * 32] = __uint_as_float((unsigned)(rec.lo >> 32));
         c[22 * 32] = __uint_as_float((unsigned)rec.hi); c[23 * 32] = __uint_as_float((unsigned)(rec.hi >> 32));
-        c[24 * 32] = ang[0];
-        if (JM != JM_REVOLUTE) { c[25 * 32] = ang[1]; c[26 * 32] = ang[2]; }
+        c[24 * 32] = ang[0]; c[25 * 32] = ang[1]; c[26 * 32] = ang[2];
+        c[27 * 32] = 0.f;  // pad: the adjoint copies whole rows
         {
             float I[9], inv_I[9];
             par_load9<NT>(par, 1, I);
@@ -886,7 +886,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     F3 g = v3<float>(M.g[0], M.g[1], M.g[2]);
     // com of the parent body (to fold the parent's world-COM adjoint into its pose adjoint in the child lane)
     stage_static(st, L, comm.parent_vec(L.com, L.parent_slot));
-    comm.sync();
+    __syncthreads();  // the static table is per block (all warps stage identical values)
 
     float a_inv_m = 0.f, a_ke[3] = {0, 0, 0}, a_kd[3] = {0, 0, 0};
 

@@ -1,0 +1,16 @@
+import sys, torch
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+from helpers import make_inputs, settle_height, make_mixed_robot
+from test_gpu_parity import flat_args, run_cuda
+from ppr_diffphys_b200 import SimEnv
+for robot in ['laikago', 'human', 'quad', make_mixed_robot()]:
+    stride, F, bs = 4, 3, 9
+    T = stride * (F - 1) + 1
+    rm, d = make_inputs(robot, bs=bs, T=T, seed=3, res_f_std=0.05, torque_std=0.05)
+    d = settle_height(rm, d, 0.003)
+    env = SimEnv(rm)
+    a, _, _ = flat_args(d, torch.device('cuda:0'))
+    pos, vel, _ = run_cuda(env, a, bs, T, stride)
+    (pos.sum() + vel.sum()).backward()
+    torch.cuda.synchronize()
+    print(rm.name, env.packing, 'ok', float(pos.abs().max()))
