@@ -196,7 +196,7 @@ def run_gpu_arm(args):
     p_ke = torch.as_tensor(rm.joint_target_ke, device=dev).clone().requires_grad_(True)
     p_kd = torch.as_tensor(rm.joint_target_kd, device=dev).clone().requires_grad_(True)
     p_mass = torch.as_tensor(rm.body_mass, device=dev).clone().requires_grad_(True)
-    packed = torch.zeros(2 * nqd + nb, device=dev)
+    packed = torch.zeros(2 * nqd + nb + 1, device=dev)   # shared-parameter gradients + the loss (one D2H read)
 
     def step(inp, need_loss_host):
         """one optimisation step of the hot path on device-resident inputs"""
@@ -216,12 +216,13 @@ def run_gpu_arm(args):
         loss.backward()
         packed[:nqd] = p_ke.grad
         packed[nqd:2 * nqd] = p_kd.grad
-        packed[2 * nqd:] = p_mass.grad
+        packed[2 * nqd:2 * nqd + nb] = p_mass.grad
+        packed[-1] = loss.detach()
         if world > 1:
             dist.all_reduce(packed)
         if need_loss_host:
-            return float(loss.detach()), packed.cpu()
-        return loss, packed
+            return packed.cpu()       # device -> host: loss + reduced shared-parameter gradients
+        return packed
 
     dev_inp = {k: v.to(dev) for k, v in host.items()}
     bytes_in = sum(host[k].numel() * 4 for k in ("q_init", "qd_init", "refs"))
@@ -305,7 +306,7 @@ def run_gpu_arm(args):
             if i + 1 < steps:
                 enqueue_copy(i + 1)
             cur.wait_event(ready[i % 2])
-            out = step(bufs[i % 2], True)       # float(loss) + packed.cpu(): device -> host every step
+            out = step(bufs[i % 2], True)       # packed.cpu(): loss + shared gradients, device -> host every step
             free[i % 2].record(cur)
         return out
 
@@ -364,7 +365,7 @@ def run_gpu_arm(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "robot": w["robot"], "envs_per_gpu": bs, "substeps_per_window": window,
                    "frame_stride": stride, "bodies": nb, "dofs": nqd, "contacts_per_env": rm.nc,
-                   "parallelism": "env-sharded x%d, 1 all-reduce of %d floats/step" % (world, 2 * nqd + nb),
+                   "parallelism": "env-sharded x%d, 1 all-reduce of %d floats/step" % (world, 2 * nqd + nb + 1),
                    "params": "per-env replicated" if args.replicate_params else "shared (un-replicated)",
                    "l2": "working set >> 126 MB L2 (state checkpoint %.2f GB/step streamed once each way)"
                          % (env.workspace_bytes(bs, nsteps) / 1e9)},
@@ -378,7 +379,7 @@ def run_gpu_arm(args):
                      "fwd_bwd_combined_frac": ab["fwdbwd"] * bs * window / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak_gbs,
                      "note": "the path is FP32-issue / latency bound, not HBM bound (SURVEY.md 8d)"},
         "e2e": {"value": env_steps / (ms_e2e / args.steps * 1e-3), "unit": "env-steps/s",
-                "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 4 + 4 * (2 * nqd + nb),
+                "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 4 * (2 * nqd + nb + 1),
                 "ms_per_step": ms_e2e / args.steps,
                 "note": "pinned-host inputs, copy of step i+1 overlapped with the kernels of step i"},
         "cpu_baseline": cpu,
