@@ -139,7 +139,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // Collectives over the articulation tree, executed by EVERY thread of the group (warp or block):
 //   parent_*  : each thread obtains values held by the thread of its parent body
 //   gather_*  : each thread sums a message held by the threads of its child bodies
-// `child` packs up to 8 child slots as bytes (0xff = none); `ps` = slot of the parent (own slot if none).
+// `child` packs up to 8 children as byte OFFSETS from the own slot (children follow their parent; 0 = none);
+// `ps` = slot of the parent (own slot if none).
 template <int NT> struct WarpComm {
     static constexpr int kThreads = NT;
     static constexpr bool kBlock = false;
@@ -169,16 +170,16 @@ template <int NT> struct WarpComm {
 #pragma unroll 1
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
-            WrenchF o = shf_wrench(mine, c == 0xffu ? 0 : (int)c);
-            if (c != 0xffu) { acc.t += o.t; acc.f += o.f; }
+            WrenchF o = shf_wrench(mine, (int)(threadIdx.x & 31) + (int)c);
+            if (c) { acc.t += o.t; acc.f += o.f; }
         }
     }
     __device__ __forceinline__ void gather_body(const BodyF& mine, unsigned long long child, int maxc, BodyF& acc) const {
 #pragma unroll 1
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
-            BodyF o = shf_body(mine, c == 0xffu ? 0 : (int)c);
-            if (c != 0xffu) body_acc(acc, o);
+            BodyF o = shf_body(mine, (int)(threadIdx.x & 31) + (int)c);
+            if (c) body_acc(acc, o);
         }
     }
     __device__ __forceinline__ void gather_body_sync(const BodyF& mine, unsigned long long child, int maxc,
@@ -285,7 +286,8 @@ template <int NT> struct BlockComm {
 #pragma unroll 1
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
-            if (c != 0xffu) {
+            if (c) {
+                c += threadIdx.x;
                 acc.t += v3<float>(msg[0 * NT + c], msg[1 * NT + c], msg[2 * NT + c]);
                 acc.f += v3<float>(msg[3 * NT + c], msg[4 * NT + c], msg[5 * NT + c]);
             }
@@ -296,7 +298,7 @@ template <int NT> struct BlockComm {
 #pragma unroll 1
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
-            if (c != 0xffu) body_acc(acc, get_body(msg, (int)c));
+            if (c) body_acc(acc, get_body(msg, (int)(threadIdx.x + c)));
         }
     }
     // plain-barrier variant for the FK adjoint (outside the substep loop)
@@ -307,7 +309,7 @@ template <int NT> struct BlockComm {
 #pragma unroll 1
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
-            if (c != 0xffu) body_acc(acc, get_body(msg, (int)c));
+            if (c) body_acc(acc, get_body(msg, (int)(threadIdx.x + c)));
         }
         __syncthreads();
     }
@@ -327,7 +329,7 @@ enum { ST_XPJ = 0, ST_QPJ = 3, ST_AXIS = 7, ST_COM = 10, ST_CPAR = 13, ST_AABB =
 struct LaneInfo {
     int env, body, parent_slot, type, ndof, depth, qs, qds, c0, c1;
     bool valid, has_parent;
-    unsigned long long child;  // slots (lane / thread ids inside the group) of the children, one byte each, 0xff none
+    unsigned long long child;  // children as byte offsets from the own slot (child body index - own body index), 0 none
     JointStatic<float> js;
     F3 com;
     float aabb[7];
@@ -351,7 +353,7 @@ __device__ __forceinline__ LaneInfo lane_setup(const DevModel& M, int64_t group,
 #pragma unroll
     for (int s = 0; s < PPR_MAX_CHILD; ++s) {
         unsigned c = (unsigned)((ch >> (8 * s)) & 0xffu);
-        unsigned long long v = (c == 0xffu || !L.valid) ? 0xffull : (unsigned long long)(seg + c);
+        unsigned long long v = (c == 0xffu || !L.valid) ? 0ull : (unsigned long long)(c - (unsigned)body);
         out |= v << (8 * s);
     }
     L.child = out;
