@@ -492,9 +492,21 @@ __device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneI
     rec.cnt = 0; rec.lo = 0ull; rec.hi = 0ull;
     const bool can_rec = M.nc <= 65535;
     if (cand == -2) {
-        for (int k = L.c0; k < L.c1; ++k) {
+        // small body (<= big_threshold <= 32 points, e.g. 8 box corners): pass 1 tests all points with four loads in
+        // flight and builds a bitmask, pass 2 evaluates only the penetrating ones (one inlined copy of the force code)
+        unsigned pen = 0;
+        for (int k0 = L.c0; k0 < L.c1; k0 += 4) {
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = (k0 + u < L.c1) ? M.cpt[k0 + u] : make_float4(0.f, 0.f, 0.f, -1e30f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (!(s.x.y + m0 * p[u].x + m1 * p[u].y + m2 * p[u].z - p[u].w > 1e-6f)) pen |= 1u << (k0 - L.c0 + u);
+        }
+        while (pen) {
+            int k = L.c0 + __ffs(pen) - 1;
+            pen &= pen - 1;
             float4 p = M.cpt[k];
-            if (s.x.y + m0 * p.x + m1 * p.y + m2 * p.z - p.w > 1e-6f) continue;  // cheap conservative reject
             if (contact_point_fwd(s, Rb, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), F)) rec_push(rec, k);
         }
     } else {
