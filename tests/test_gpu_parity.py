@@ -370,3 +370,47 @@ def test_joint_X_p_setter_changes_fk():
     env.joint_X_p = xp
     b1, _ = env.fk(q, qd)
     assert abs(float(b1[0, 1, 0] - b0[0, 1, 0]) - 0.1) < 1e-6
+
+
+def test_forward_kinematics_reference_quirks():
+    """dp_model.py:1030-1035,1080-1082: CPU inputs are moved to the GPU and the outputs back; :1109-1110 the
+    gradient is scrubbed NaN -> 0 and clamped from ABOVE at +1 only."""
+    from ppr_diffphys_b200 import ForwardKinematics, SimEnv
+    env = SimEnv("laikago")
+    T, bs = 2, 3
+    rm, d = make_inputs("laikago", bs=T * bs, T=1, seed=4, ang=0.5)
+    q = d["q_init"].float().view(T, bs, -1).clone().requires_grad_(True)       # CPU tensors
+    qd = d["qd_init"].float().view(T, bs, -1).clone().requires_grad_(True)
+    bq, bqd, frames = ForwardKinematics.apply(q, qd, env)
+    assert not bq.is_cuda and bq.shape == (bs, T, rm.nb, 7)
+    (bq[..., 0].sum() * 50.0 - bq[..., 1].sum() * 50.0).backward()             # +-50 per body on root x / y
+    g = q.grad
+    assert not g.is_cuda and torch.isfinite(g).all()
+    assert float(g.max()) == 1.0                 # 13 bodies x 50 on root x -> clamped to +1
+    assert float(g.min()) < -100.0               # no lower clamp (reference quirk)
+
+
+def test_record_forces_flag_and_last_step_skip():
+    from ppr_diffphys_b200 import SimEnv
+    stride, F, bs = 8, 3, 4
+    T = stride * (F - 1) + 1
+    rm, d = make_inputs("human", bs=bs, T=T, seed=6)
+    d = settle_height(rm, d, 0.003)
+    dev = torch.device("cuda:0")
+    env = SimEnv(rm)
+    from ppr_diffphys_b200 import ForwardWarp
+    outs = []
+    for rec in (True, False):
+        a, _, _ = flat_args(d, dev, requires_grad=False)
+        caller = Caller(env, bs, T, stride)
+        caller.record_forces = rec
+        pos, vel = ForwardWarp.apply(a["q_init"], a["qd_init"], a["torques"], a["res_f"], a["refs"], a["target_ke"],
+                                     a["target_kd"], a["body_mass"], a["body_inv_mass"], a["body_inertia"],
+                                     a["body_inv_inertia"], caller)
+        outs.append((pos, vel, caller))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert len(outs[0][2].grfs) == F and len(outs[1][2].grfs) == 0
+    # grf = body_f after the contact pass: fn = c * ke < 0 is SUBTRACTED (integrator_euler.py:147,179), i.e. bodies in
+    # contact carry an upward (+y) force
+    grf = torch.stack(outs[0][2].grfs)
+    assert float(grf[..., 4].max()) > 1.0 and float(grf[..., 4].min()) >= 0.0 and torch.isfinite(grf).all()
