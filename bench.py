@@ -187,6 +187,8 @@ def run_gpu_arm(args):
     nsteps = window + 1
     rm = load_robot(w["robot"])
     env = SimEnv(rm)
+    if args.ckpt_every > 1:
+        env.set_checkpoint_every(args.ckpt_every)
     nb, nqd = rm.nb, rm.nqd
     caller = Caller(env, bs, nsteps, stride)
     host = make_batch(env, bs, nsteps, seed=rank, clearance=w["clearance"], lin_vel=w["lin_vel"], pinned_host=True)
@@ -367,6 +369,7 @@ def run_gpu_arm(args):
                    "frame_stride": stride, "bodies": nb, "dofs": nqd, "contacts_per_env": rm.nc,
                    "parallelism": "env-sharded x%d, 1 all-reduce of %d floats/step" % (world, 2 * nqd + nb + 1),
                    "params": "per-env replicated" if args.replicate_params else "shared (un-replicated)",
+                   "checkpoint_every": args.ckpt_every,
                    "l2": "working set >> 126 MB L2 (state checkpoint %.2f GB/step streamed once each way)"
                          % (env.workspace_bytes(bs, nsteps) / 1e9)},
         "gpu_launches": int(launches),
@@ -399,6 +402,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--ckpt-every", type=int, default=1,
+                    help="checkpoint policy K: keep the state every K substeps, recompute the rest in the adjoint")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the other_configs context measurements")
     ap.add_argument("--replicate-params", action="store_true",

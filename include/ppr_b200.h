@@ -65,6 +65,11 @@ int ppr_model_destroy(ppr_model_t m);
 int ppr_model_set_joint_X_p(ppr_model_t m, const float* joint_X_p, void* stream);
 int ppr_model_set_attach(ppr_model_t m, float attach_ke, float attach_kd);
 int ppr_model_set_gravity(ppr_model_t m, const float g[3]);
+/* Checkpoint policy of the rollout (default 1): the forward pass keeps the per-substep state every `every` substeps;
+ * the adjoint re-computes the substeps in between, segment by segment (costs (every-1)/every of a forward pass,
+ * shrinks the workspace `every`-fold).  The reference keeps one full Warp State + gradient mirror per substep
+ * (dp_model.py:396-399).  Must be set before ppr_rollout_workspace_bytes / _forward and unchanged until _backward. */
+int ppr_model_set_checkpoint_every(ppr_model_t m, int32_t every);
 /* introspection of the environment packing chosen for this articulation: a group is a warp (32 threads) or a
  * thread block (96 / 160 threads); each group hosts floor(threads / nb) environments, one thread per body. */
 int ppr_model_envs_per_group(ppr_model_t m);

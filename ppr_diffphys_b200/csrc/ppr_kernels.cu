@@ -71,6 +71,7 @@ struct ppr_model {
     size_t xpj_offset;        // byte offset of xpj inside blob
     std::vector<float> h_xpj;
     int variant;              // 0: FREE+REVOLUTE, 1: FREE+COMPOUND (both: no limits, identity q_off), 2: generic
+    int ckpt_every;           // checkpoint policy K (1 = every substep, the fast default)
     int comm;                 // env packing of the rollout kernels: 0 per warp (128-thread blocks), 1 per 96-thread
                               // block, 2 per 160-thread block
 };
@@ -686,6 +687,7 @@ fk_backward_kernel(DevModel M, int64_t n, const float* __restrict__ q, const flo
 // ----------------------------------------------------------------------------------------------- rollout
 struct RolloutArgs {
     int64_t bs, nsteps, stride, nwarps, ngroups;
+    int64_t ckpt_every;  // K: a checkpoint row is kept every K substeps; the adjoint recomputes the K-1 in between
     float dt;
     int pstride;  // 1: per-env parameter arrays, 0: one shared copy
     const float *q_init, *qd_init, *torques, *res_f, *refs, *ke, *kd, *inv_m, *I, *inv_I;
@@ -836,8 +838,9 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         warp_forces<JM, LIMITS, QOFF>(comm, M, L, lane, s, Rb, xc, ctl, cm0, st, clist, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
                     (frame && A.out_grf) ? A.out_grf + frow * 6 : nullptr,
                     (frame && A.out_jaf) ? A.out_jaf + frow * 6 : nullptr, F, rec, ang);
-        // checkpoint (coalesced: component-major rows of 32 lanes)
-        float* c = ck + t * ck_step;
+        // checkpoint (coalesced: component-major rows of 32 lanes), every K-th substep
+        if (t % A.ckpt_every == 0) {
+        float* c = ck + (t / A.ckpt_every) * ck_step;
         c[0 * 32] = s.x.x; c[1 * 32] = s.x.y; c[2 * 32] = s.x.z;
         c[3 * 32] = s.r.x; c[4 * 32] = s.r.y; c[5 * 32] = s.r.z; c[6 * 32] = s.r.w;
         c[7 * 32] = s.w.x; c[8 * 32] = s.w.y; c[9 * 32] = s.w.z;
@@ -849,6 +852,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         c[22 * 32] = __uint_as_float((unsigned)rec.hi); c[23 * 32] = __uint_as_float((unsigned)(rec.hi >> 32));
         c[24 * 32] = ang[0]; c[25 * 32] = ang[1]; c[26 * 32] = ang[2];
         c[27 * 32] = 0.f;  // pad: the adjoint copies whole rows
+        }
         {
             float I[9], inv_I[9];
             par_load9<NT>(par, 1, I);
@@ -858,7 +862,11 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     }
 }
 
-template <class Comm, int JM, bool LIMITS, bool QOFF>
+// RECOMP = false: every substep has a checkpoint row (K = 1).  RECOMP = true: rows exist every K substeps; before a
+// segment of K substeps is differentiated its rows are RE-COMPUTED from the segment's first state with the forward
+// step function and parked in a per-warp scratch area of the workspace (K rows), then consumed exactly like
+// stored rows.  Costs (K-1)/K of a forward pass, shrinks the checkpoint K-fold.
+template <class Comm, int JM, bool LIMITS, bool QOFF, bool RECOMP>
 __global__ void __launch_bounds__(Comm::kThreads, PPR_BWD_MINB(Comm::kThreads))
 rollout_backward_kernel(DevModel M, RolloutArgs A) {
     constexpr int NT = Comm::kThreads;
@@ -904,9 +912,13 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
 
     float a_inv_m = 0.f, a_ke[3] = {0, 0, 0}, a_kd[3] = {0, 0, 0};
 
-    const float* ckw = A.ckpt + (warp * PPR_CKPT_FLOATS) * 32;  // this warp's rows (3 kB each, 16-byte aligned)
+    const float* ckw = A.ckpt + (warp * PPR_CKPT_FLOATS) * 32;  // this warp's rows (3.5 kB each, 16-byte aligned)
     const int64_t ck_step = A.nwarps * PPR_CKPT_FLOATS * 32;
     const int64_t last = A.nsteps - 1;
+    const int64_t K = RECOMP ? A.ckpt_every : 1;
+    // scratch rows of this warp (RECOMP): behind the ceil(nsteps / K) stored rows of all warps
+    float* scr = A.ckpt + ((A.nsteps + K - 1) / K) * ck_step + warp * K * PPR_CKPT_FLOATS * 32;
+    bool prefetched = false;
 
     BodyF adjN = body_zero<float>();
     // rows of the never-differentiated last substep (dp_model.py:397): zero gradient
@@ -935,8 +947,52 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         }
         if (t == 0) break;
         int64_t tp = t - 1;  // differentiate substep tp -> t
-        if (t == last) {     // first row: nothing was prefetched yet
-            cp_async_row(roww, ckw + tp * ck_step, lane);
+        const int64_t seg_lo = (tp / K) * K;   // first substep of the segment tp belongs to (K = 1: tp itself)
+        if (RECOMP && (tp == last - 1 || tp % K == K - 1)) {
+            // ---- re-run substeps seg_lo .. tp from the stored state and park their rows in the scratch area
+            const float* c0 = ckw + (seg_lo / K) * ck_step + lane;
+            BodyF sr;
+            sr.x = v3<float>(c0[0 * 32], c0[1 * 32], c0[2 * 32]);
+            sr.r = q4<float>(c0[3 * 32], c0[4 * 32], c0[5 * 32], c0[6 * 32]);
+            sr.w = v3<float>(c0[7 * 32], c0[8 * 32], c0[9 * 32]);
+            sr.v = v3<float>(c0[10 * 32], c0[11 * 32], c0[12 * 32]);
+            for (int64_t tr = seg_lo; tr <= tp; ++tr) {
+                const F3 comr = st_vec3(st, ST_COM, L.body);
+                const M3F Rr = qmat(sr.r);
+                F3 xcr = sr.x + mrot(Rr, comr);
+                load_ctl(M, L, A, tr, ke, kd, ctl);
+                WrenchF Fr;
+                ContactRec recr;
+                float angr[3];
+                warp_forces<JM, LIMITS, QOFF>(comm, M, L, lane, sr, Rr, xcr, ctl, cm0, st, clist,
+                                              A.res_f ? A.res_f + ((tr * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
+                                              nullptr, nullptr, Fr, recr, angr);
+                float* c = scr + (tr - seg_lo) * PPR_CKPT_FLOATS * 32 + lane;
+                c[0 * 32] = sr.x.x; c[1 * 32] = sr.x.y; c[2 * 32] = sr.x.z;
+                c[3 * 32] = sr.r.x; c[4 * 32] = sr.r.y; c[5 * 32] = sr.r.z; c[6 * 32] = sr.r.w;
+                c[7 * 32] = sr.w.x; c[8 * 32] = sr.w.y; c[9 * 32] = sr.w.z;
+                c[10 * 32] = sr.v.x; c[11 * 32] = sr.v.y; c[12 * 32] = sr.v.z;
+                c[13 * 32] = Fr.t.x; c[14 * 32] = Fr.t.y; c[15 * 32] = Fr.t.z;
+                c[16 * 32] = Fr.f.x; c[17 * 32] = Fr.f.y; c[18 * 32] = Fr.f.z;
+                c[19 * 32] = __uint_as_float(recr.cnt);
+                c[20 * 32] = __uint_as_float((unsigned)recr.lo); c[21 * 32] = __uint_as_float((unsigned)(recr.lo >> 32));
+                c[22 * 32] = __uint_as_float((unsigned)recr.hi); c[23 * 32] = __uint_as_float((unsigned)(recr.hi >> 32));
+                c[24 * 32] = angr[0]; c[25 * 32] = angr[1]; c[26 * 32] = angr[2];
+                c[27 * 32] = 0.f;
+                if (tr < tp) {
+                    float I[9], inv_I[9];
+                    par_load9<NT>(par, 1, I);
+                    par_load9<NT>(par, 10, inv_I);
+                    sr = integrate_fwd(sr, Rr, xcr, comr, Fr, par[0], I, inv_I, g, A.dt);
+                }
+            }
+            __threadfence_block();
+            __syncwarp();   // the rows are read back (by other lanes) through cp.async
+            prefetched = false;
+        }
+        const float* rowsrc = RECOMP ? scr + (tp - seg_lo) * PPR_CKPT_FLOATS * 32 : ckw + tp * ck_step;
+        if (!prefetched) {   // first row (of the segment): nothing was prefetched yet
+            cp_async_row(roww, rowsrc, lane);
             cp_async_commit();
         }
         cp_async_wait_all();
@@ -957,9 +1013,10 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         ang[0] = row[24 * 32];
         ang[1] = JM != JM_REVOLUTE ? row[25 * 32] : 0.f;
         ang[2] = JM != JM_REVOLUTE ? row[26 * 32] : 0.f;
-        __syncwarp();        // everyone has read the row: refill it with the next (earlier) one
-        if (tp > 0) {
-            cp_async_row(roww, ckw + (tp - 1) * ck_step, lane);
+        __syncwarp();        // everyone has read the row: refill it with the next (earlier) one of the segment
+        prefetched = RECOMP ? (tp > seg_lo) : (tp > 0);
+        if (prefetched) {
+            cp_async_row(roww, RECOMP ? rowsrc - PPR_CKPT_FLOATS * 32 : ckw + (tp - 1) * ck_step, lane);
             cp_async_commit();
         }
         const F3 com = st_vec3(st, ST_COM, L.body);
@@ -1193,6 +1250,7 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
         const char* ov = getenv("PPR_COMM");
         if (ov && ov[0] >= '0' && ov[0] <= '2') m->comm = ov[0] - '0';
     }
+    m->ckpt_every = 1;
     m->xpj_offset = o_xpj;
     m->h_xpj.assign(D->joint_X_p, D->joint_X_p + nb * 7);
     m->magic = PPR_MAGIC;
@@ -1225,6 +1283,12 @@ extern "C" int ppr_model_set_gravity(ppr_model_t m, const float g[3]) {
     if (!check(m)) return PPR_E_HANDLE;
     if (!g) return PPR_E_ARG;
     m->d.g[0] = g[0]; m->d.g[1] = g[1]; m->d.g[2] = g[2];
+    return 0;
+}
+extern "C" int ppr_model_set_checkpoint_every(ppr_model_t m, int32_t every) {
+    if (!check(m)) return PPR_E_HANDLE;
+    if (every < 1 || every > 4096) return PPR_E_ARG;
+    m->ckpt_every = every;
     return 0;
 }
 extern "C" int ppr_model_envs_per_group(ppr_model_t m) {
@@ -1270,24 +1334,24 @@ template <class K> static cudaError_t launch_rollout(K kernel, size_t smem, unsi
     kernel<<<grid, nt, smem, st>>>(d, A);
     return cudaGetLastError();
 }
-#define PPR_LAUNCH_ROLLOUT(KERNEL, ADJ)                                                                              \
+#define PPR_LAUNCH_ROLLOUT(KERNEL, ADJ, ...)                                                                              \
     do {                                                                                                             \
         cudaError_t e_;                                                                                              \
         if (m->comm == 0) {                                                                                          \
             typedef WarpComm<128> C_;                                                                                \
-            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, m->d, A); \
-            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, m->d, A); \
-            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, m->d, A); \
+            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, m->d, A); \
+            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, m->d, A); \
+            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, m->d, A); \
         } else if (m->comm == 1) {                                                                                   \
             typedef BlockComm<96> C_;                                                                                \
-            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, m->d, A); \
-            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, m->d, A); \
-            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, m->d, A); \
+            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, m->d, A); \
+            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, m->d, A); \
+            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, m->d, A); \
         } else {                                                                                                     \
             typedef BlockComm<160> C_;                                                                               \
-            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, m->d, A); \
-            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, m->d, A); \
-            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, m->d, A); \
+            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, m->d, A); \
+            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, m->d, A); \
+            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, m->d, A); \
         }                                                                                                            \
         g_launches++;                                                                                                \
         return (int)e_;                                                                                              \
@@ -1326,7 +1390,9 @@ extern "C" size_t ppr_rollout_workspace_bytes(ppr_model_t m, int64_t bs, int64_t
     if (!check(m) || bs <= 0 || nsteps <= 0) return 0;
     int64_t ngroups, nwarps; unsigned grid;
     rollout_geometry(m, bs, ngroups, nwarps, grid);
-    return (size_t)nwarps * (size_t)nsteps * PPR_CKPT_FLOATS * 32 * sizeof(float);
+    const int64_t K = m->ckpt_every;
+    const int64_t rows = (nsteps + K - 1) / K + (K > 1 ? K : 0);   // stored rows + per-warp scratch rows
+    return (size_t)nwarps * (size_t)rows * PPR_CKPT_FLOATS * 32 * sizeof(float);
 }
 
 extern "C" int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t stride, float dt,
@@ -1344,13 +1410,13 @@ extern "C" int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, in
     memset(&A, 0, sizeof(A));
     unsigned grid;
     rollout_geometry(m, bs, A.ngroups, A.nwarps, grid);
-    A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.dt = dt;
+    A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.dt = dt; A.ckpt_every = m->ckpt_every;
     A.pstride = shared_params ? 0 : 1;
     A.q_init = q_init; A.qd_init = qd_init; A.torques = torques; A.res_f = res_f; A.refs = refs; A.ke = ke; A.kd = kd;
     A.inv_m = inv_m; A.I = I; A.inv_I = inv_I;
     A.out_pos = out_pos; A.out_vel = out_vel; A.out_grf = out_grf; A.out_jaf = out_jaf; A.ckpt = (float*)ws;
     cudaStream_t st = (cudaStream_t)stream;
-    PPR_LAUNCH_ROLLOUT(rollout_forward_kernel, false);
+    PPR_LAUNCH_ROLLOUT(rollout_forward_kernel, false, );
 }
 
 extern "C" int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t stride, float dt,
@@ -1371,7 +1437,7 @@ extern "C" int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, i
     memset(&A, 0, sizeof(A));
     unsigned grid;
     rollout_geometry(m, bs, A.ngroups, A.nwarps, grid);
-    A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.dt = dt;
+    A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.dt = dt; A.ckpt_every = m->ckpt_every;
     A.pstride = shared_params ? 0 : 1;
     A.q_init = q_init; A.qd_init = qd_init; A.torques = torques; A.res_f = res_f; A.refs = refs; A.ke = ke; A.kd = kd;
     A.inv_m = inv_m; A.I = I; A.inv_I = inv_I; A.ckpt = (float*)ws;
@@ -1379,5 +1445,6 @@ extern "C" int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, i
     A.adj_torques = adj_torques; A.adj_res_f = adj_res_f; A.adj_refs = adj_refs; A.adj_ke = adj_ke; A.adj_kd = adj_kd;
     A.adj_inv_m = adj_inv_m; A.adj_I = adj_I; A.adj_inv_I = adj_inv_I;
     cudaStream_t st = (cudaStream_t)stream;
-    PPR_LAUNCH_ROLLOUT(rollout_backward_kernel, true);
+    if (m->ckpt_every > 1) PPR_LAUNCH_ROLLOUT(rollout_backward_kernel, true, , true);
+    PPR_LAUNCH_ROLLOUT(rollout_backward_kernel, true, , false);
 }
