@@ -70,7 +70,13 @@ int ppr_model_set_gravity(ppr_model_t m, const float g[3]);
  * shrinks the workspace `every`-fold).  The reference keeps one full Warp State + gradient mirror per substep
  * (dp_model.py:396-399).  Must be set before ppr_rollout_workspace_bytes / _forward and unchanged until _backward. */
 int ppr_model_set_checkpoint_every(ppr_model_t m, int32_t every);
-/* introspection of the environment packing chosen for this articulation: a group is a warp (32 threads) or a
+/* Rollouts of at most `max_envs` environments use the LATENCY layout (one environment per warp: the substep
+ * latency, not the issue rate, bounds a batch that cannot fill the GPU -- the reference's own shapes, 10..64 envs x
+ * 760 substeps, dp_model.py:354-367); larger ones use the throughput packing below.  Default 1024
+ * (about two warps per scheduler of a B200, the measured break-even); 0 disables.  Same rule as the checkpoint policy: set before workspace_bytes. */
+int ppr_model_set_latency_envs(ppr_model_t m, int64_t max_envs);
+int64_t ppr_model_latency_envs(ppr_model_t m);
+/* introspection of the THROUGHPUT packing chosen for this articulation: a group is a warp (32 threads) or a
  * thread block (96 / 160 threads); each group hosts floor(threads / nb) environments, one thread per body. */
 int ppr_model_envs_per_group(ppr_model_t m);
 int ppr_model_group_threads(ppr_model_t m);

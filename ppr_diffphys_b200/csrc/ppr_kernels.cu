@@ -72,6 +72,7 @@ struct ppr_model {
     std::vector<float> h_xpj;
     int variant;              // 0: FREE+REVOLUTE, 1: FREE+COMPOUND (both: no limits, identity q_off), 2: generic
     int ckpt_every;           // checkpoint policy K (1 = every substep, the fast default)
+    int64_t latency_envs;     // batches up to this many envs run one env per warp (latency layout)
     int comm;                 // env packing of the rollout kernels: 0 per warp (128-thread blocks), 1 per 96-thread
                               // block, 2 per 160-thread block
 };
@@ -149,7 +150,7 @@ template <int NT> struct WarpComm {
     __device__ __forceinline__ explicit WarpComm(float*) {}
     static __device__ __forceinline__ int64_t group() { return ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; }
     static __device__ __forceinline__ int slot() { return threadIdx.x & 31; }
-    static __device__ __forceinline__ int envs_per_group(const DevModel& M) { return 32 / M.nb; }
+    static __device__ __forceinline__ int envs_per_group(const DevModel& M) { return M.epw; }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     __device__ __forceinline__ BodyF parent_body(const BodyF& s, int ps) const { return shf_body(s, ps); }
     __device__ __forceinline__ F3 parent_vec(F3 v, int ps) const { return shf3(v, ps); }
@@ -1251,6 +1252,8 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
         if (ov && ov[0] >= '0' && ov[0] <= '2') m->comm = ov[0] - '0';
     }
     m->ckpt_every = 1;
+    m->latency_envs = 1024;   // ~148 SMs x 4 schedulers x 2 warps: measured break-even of the two layouts on B200
+    if (const char* e = getenv("PPR_LATENCY_ENVS")) m->latency_envs = atoll(e);
     m->xpj_offset = o_xpj;
     m->h_xpj.assign(D->joint_X_p, D->joint_X_p + nb * 7);
     m->magic = PPR_MAGIC;
@@ -1291,6 +1294,13 @@ extern "C" int ppr_model_set_checkpoint_every(ppr_model_t m, int32_t every) {
     m->ckpt_every = every;
     return 0;
 }
+extern "C" int ppr_model_set_latency_envs(ppr_model_t m, int64_t max_envs) {
+    if (!check(m)) return PPR_E_HANDLE;
+    if (max_envs < 0) return PPR_E_ARG;
+    m->latency_envs = max_envs;
+    return 0;
+}
+extern "C" int64_t ppr_model_latency_envs(ppr_model_t m) { return check(m) ? m->latency_envs : PPR_E_HANDLE; }
 extern "C" int ppr_model_envs_per_group(ppr_model_t m) {
     if (!check(m)) return PPR_E_HANDLE;
     return m->comm == 0 ? m->d.epw : kCommThreads[m->comm] / m->d.nb;
@@ -1302,10 +1312,18 @@ extern "C" int ppr_model_group_threads(ppr_model_t m) {
 
 static inline int64_t nwarps_for(const DevModel& d, int64_t n) { return (n + d.epw - 1) / d.epw; }
 // rollout kernels: groups (warps or blocks) and warps (each owns one checkpoint row per substep)
-static inline void rollout_geometry(const ppr_model* m, int64_t bs, int64_t& ngroups, int64_t& nwarps, unsigned& grid) {
-    const int nt = kCommThreads[m->comm];
-    if (m->comm == 0) {
-        ngroups = nwarps_for(m->d, bs);
+// Small batches cannot fill 148 SMs x 4 schedulers, so what counts is the LATENCY of one substep, and that grows with
+// the number of environments a warp serialises in the contact phase: below `latency_envs` environments every
+// environment gets a warp of its own (warp layout, 1 env per warp) whatever the throughput layout of the model is.
+// A pure function of (model, bs): the three entry points of one rollout derive the same geometry.
+static inline void rollout_geometry(const ppr_model* m, int64_t bs, int64_t& ngroups, int64_t& nwarps, unsigned& grid,
+                                    int& comm, int& epw) {
+    comm = m->comm;
+    epw = m->d.epw;
+    if (bs <= m->latency_envs) { comm = 0; epw = 1; }
+    const int nt = kCommThreads[comm];
+    if (comm == 0) {
+        ngroups = (bs + epw - 1) / epw;
         grid = (unsigned)((ngroups * 32 + nt - 1) / nt);
         nwarps = ngroups;
     } else {
@@ -1337,21 +1355,23 @@ template <class K> static cudaError_t launch_rollout(K kernel, size_t smem, unsi
 #define PPR_LAUNCH_ROLLOUT(KERNEL, ADJ, ...)                                                                              \
     do {                                                                                                             \
         cudaError_t e_;                                                                                              \
-        if (m->comm == 0) {                                                                                          \
+        DevModel d_ = m->d;                                                                                          \
+        d_.epw = epw_;                                                                                               \
+        if (comm_ == 0) {                                                                                            \
             typedef WarpComm<128> C_;                                                                                \
-            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, m->d, A); \
-            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, m->d, A); \
-            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, m->d, A); \
-        } else if (m->comm == 1) {                                                                                   \
+            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, d_, A); \
+            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, d_, A); \
+            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, d_, A); \
+        } else if (comm_ == 1) {                                                                                     \
             typedef BlockComm<96> C_;                                                                                \
-            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, m->d, A); \
-            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, m->d, A); \
-            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, m->d, A); \
+            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, d_, A); \
+            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, d_, A); \
+            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, d_, A); \
         } else {                                                                                                     \
             typedef BlockComm<160> C_;                                                                               \
-            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, m->d, A); \
-            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, m->d, A); \
-            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, m->d, A); \
+            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, d_, A); \
+            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, d_, A); \
+            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, d_, A); \
         }                                                                                                            \
         g_launches++;                                                                                                \
         return (int)e_;                                                                                              \
@@ -1388,8 +1408,8 @@ extern "C" int ppr_fk_backward(ppr_model_t m, int64_t n, const float* q, const f
 
 extern "C" size_t ppr_rollout_workspace_bytes(ppr_model_t m, int64_t bs, int64_t nsteps) {
     if (!check(m) || bs <= 0 || nsteps <= 0) return 0;
-    int64_t ngroups, nwarps; unsigned grid;
-    rollout_geometry(m, bs, ngroups, nwarps, grid);
+    int64_t ngroups, nwarps; unsigned grid; int comm_, epw_;
+    rollout_geometry(m, bs, ngroups, nwarps, grid, comm_, epw_);
     const int64_t K = m->ckpt_every;
     const int64_t rows = (nsteps + K - 1) / K + (K > 1 ? K : 0);   // stored rows + per-warp scratch rows
     return (size_t)nwarps * (size_t)rows * PPR_CKPT_FLOATS * 32 * sizeof(float);
@@ -1408,8 +1428,8 @@ extern "C" int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, in
     if (ws_bytes < ppr_rollout_workspace_bytes(m, bs, nsteps)) return PPR_E_WORKSPACE;
     RolloutArgs A;
     memset(&A, 0, sizeof(A));
-    unsigned grid;
-    rollout_geometry(m, bs, A.ngroups, A.nwarps, grid);
+    unsigned grid; int comm_, epw_;
+    rollout_geometry(m, bs, A.ngroups, A.nwarps, grid, comm_, epw_);
     A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.dt = dt; A.ckpt_every = m->ckpt_every;
     A.pstride = shared_params ? 0 : 1;
     A.q_init = q_init; A.qd_init = qd_init; A.torques = torques; A.res_f = res_f; A.refs = refs; A.ke = ke; A.kd = kd;
@@ -1435,8 +1455,8 @@ extern "C" int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, i
     if (ws_bytes < ppr_rollout_workspace_bytes(m, bs, nsteps)) return PPR_E_WORKSPACE;
     RolloutArgs A;
     memset(&A, 0, sizeof(A));
-    unsigned grid;
-    rollout_geometry(m, bs, A.ngroups, A.nwarps, grid);
+    unsigned grid; int comm_, epw_;
+    rollout_geometry(m, bs, A.ngroups, A.nwarps, grid, comm_, epw_);
     A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.dt = dt; A.ckpt_every = m->ckpt_every;
     A.pstride = shared_params ? 0 : 1;
     A.q_init = q_init; A.qd_init = qd_init; A.torques = torques; A.res_f = res_f; A.refs = refs; A.ke = ke; A.kd = kd;

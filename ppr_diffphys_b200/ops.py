@@ -122,6 +122,14 @@ class SimEnv:
         _lib.check(self._lib.ppr_model_set_checkpoint_every(self._h, int(every)), "ppr_model_set_checkpoint_every")
         self.checkpoint_every = int(every)
 
+    def set_latency_envs(self, max_envs):
+        """Batches of at most ``max_envs`` environments run one environment per warp (lowest substep latency)."""
+        _lib.check(self._lib.ppr_model_set_latency_envs(self._h, int(max_envs)), "ppr_model_set_latency_envs")
+
+    @property
+    def latency_envs(self):
+        return int(self._lib.ppr_model_latency_envs(self._h))
+
     @property
     def packing(self):
         """(threads per group, environments per group): a group is a warp or a thread block."""

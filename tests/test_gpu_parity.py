@@ -26,6 +26,15 @@ POS_TOL, GRAD_RTOL = 1e-4, 1e-3
 GRAD_RTOL_STIFF = 2e-2
 
 
+@pytest.fixture(autouse=True, params=["throughput-layout", "latency-layout"])
+def layout(request, monkeypatch):
+    """Every test of this file runs under both environment packings: the block / warp packing used for batches
+    that fill the GPU, and the one-environment-per-warp layout small batches get by default (PPR_LATENCY_ENVS is
+    read by ppr_model_create)."""
+    monkeypatch.setenv("PPR_LATENCY_ENVS", "0" if request.param == "throughput-layout" else "1000000")
+    return request.param
+
+
 class Caller:
     """Stand-in for the reference's ``phys_model`` object handed to ForwardWarp.apply (dp_model.py:733-746)."""
 
@@ -358,6 +367,38 @@ def test_checkpoint_every_k_recompute(robot, every):
         env.set_checkpoint_every(0)
 
 
+@pytest.mark.parametrize("robot", ["laikago", "human", "quad", "mixed"])
+def test_latency_layout_equals_throughput_layout(robot):
+    """Small batches run one environment per warp (ppr_model_set_latency_envs), large ones the block / warp packing
+    chosen for throughput: same arithmetic per body, so trajectories and force side channels agree bit for bit and
+    gradients to rounding."""
+    from ppr_diffphys_b200 import SimEnv
+    stride, F, bs = 16, 3, 11
+    T = stride * (F - 1) + 1
+    if robot == "mixed":
+        rm, d = make_inputs(make_mixed_robot(), bs=bs, T=T, seed=4, ang=0.25, res_f_std=0.05, torque_std=0.05,
+                            lin_vel=0.3, qd_std=0.05)
+        d = settle_height(rm, d, 0.004)
+    else:
+        rm, d = make_inputs(robot, bs=bs, T=T, seed=33)
+        d = settle_height(rm, d, 0.002)
+    dev = torch.device("cuda:0")
+    out = []
+    for lat in (0, 1 << 20):
+        env = SimEnv(rm)
+        env.set_latency_envs(lat)
+        a, _, _ = flat_args(d, dev)
+        pos, vel, caller = run_cuda(env, a, bs, T, stride)
+        ((pos ** 2).sum() + (vel ** 2).sum() * 0.01).backward()
+        out.append((pos.detach(), vel.detach(), torch.stack(caller.grfs), torch.stack(caller.jafs),
+                    [a[k].grad for k in KEYS]))
+    for x, y in zip(out[0][:4], out[1][:4]):
+        assert torch.equal(x, y)
+    # the adjoint instances of the two layouts are separate compilations (different fma contraction): last-bit level
+    for k, x, y in zip(KEYS, out[0][4], out[1][4]):
+        assert rel(x, y.double().cpu()) < 1e-5, k
+
+
 def test_single_frame_window_and_single_env():
     from oracle import sim_oracle as so
     from ppr_diffphys_b200 import SimEnv
@@ -373,8 +414,9 @@ def test_single_frame_window_and_single_env():
     assert torch.isfinite(a["q_init"].grad).all() and float(a["refs"].grad.abs().max()) == 0.0
 
 
-def test_c_abi_error_codes():
+def test_c_abi_error_codes(monkeypatch):
     from ppr_diffphys_b200 import SimEnv, _lib
+    monkeypatch.delenv("PPR_LATENCY_ENVS")
     lib = _lib.lib()
     env = SimEnv("laikago")
     h = env._h
@@ -389,7 +431,11 @@ def test_c_abi_error_codes():
     assert lib.ppr_rollout_forward(h, 0, 65, 32, C.c_float(5e-4), 0, *args, p, C.c_size_t(16), n) == 0   # empty batch
     threads, epg = env.packing
     assert threads in (32, 96, 160) and epg == threads // env.nb
+    assert env.latency_envs == 1024
+    assert lib.ppr_rollout_workspace_bytes(h, 2, 65) == 2 * 65 * 28 * 32 * 4          # latency layout: 1 env per warp
+    env.set_latency_envs(0)
     assert lib.ppr_rollout_workspace_bytes(h, 2, 65) == -(-2 // epg) * (threads // 32) * 65 * 28 * 32 * 4
+    assert lib.ppr_model_set_latency_envs(h, -1) == -1
     before = _lib.launch_count()
     env.fk(torch.zeros(3, env.nq, device="cuda"), torch.zeros(3, env.nqd, device="cuda"))
     assert _lib.launch_count() == before + 1
