@@ -132,8 +132,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     unsigned ok;
     do {
+#ifdef PPR_MBAR_HINT_NS
+        // suspend-time hint: the thread may sleep in hardware up to this long before try_wait returns false, so a long
+        // wait costs a handful of polls instead of hundreds of issue slots taken from the other resident warps
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity), "r"((unsigned)PPR_MBAR_HINT_NS) : "memory");
+#else
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+#endif
     } while (!ok);
 }
 
@@ -198,13 +205,18 @@ template <int NT> struct WarpComm {
 template <int NT> struct BlockComm {
     static constexpr int kThreads = NT;
     static constexpr bool kBlock = true;
-    static constexpr int kExFloats = (22 + 13) * NT + 4;  // + two 8-byte mbarriers
-    float* ex;   // [22][NT]
-    float* msg;  // [13][NT]
+    // exchange areas are arrays of float4 [k][NT] (thread t's k-th quad at [k * NT + t]): one LDS.128 / STS.128 moves
+    // what four scalar accesses did, conflict-free because consecutive threads touch consecutive 16-byte slots
+    static constexpr int kExQuads = 6;   // body 13 + world COM 3 = 4 quads, wrench 6 (+2 pad) = 2 quads
+    static constexpr int kMsgQuads = 4;  // body 13 (+3 pad) or wrench 6 (+2 pad)
+    static constexpr int kExFloats = (kExQuads + kMsgQuads) * 4 * NT + 4;  // + two 8-byte mbarriers
+    float4* ex;
+    float4* msg;
     unsigned long long* bar;  // [0]: `ex` published, [1]: `msg` published
     unsigned phA, phB;
     __device__ __forceinline__ explicit BlockComm(float* sm)
-        : ex(sm), msg(sm + 22 * NT), bar((unsigned long long*)(sm + 35 * NT)), phA(0), phB(0) {}
+        : ex((float4*)sm), msg((float4*)sm + kExQuads * NT),
+          bar((unsigned long long*)(sm + (kExQuads + kMsgQuads) * 4 * NT)), phA(0), phB(0) {}
     __device__ __forceinline__ void init() {
         if (threadIdx.x == 0) { mbar_init(bar, NT); mbar_init(bar + 1, NT); }
         __syncthreads();
@@ -213,74 +225,80 @@ template <int NT> struct BlockComm {
     static __device__ __forceinline__ int slot() { return threadIdx.x; }
     static __device__ __forceinline__ int envs_per_group(const DevModel& M) { return NT / M.nb; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
-    __device__ __forceinline__ void put_body(float* a, const BodyF& s) const {
+    // quads 0..3 of a body; the last three floats of quad 3 carry `tail` (the world COM in the state exchange)
+    __device__ __forceinline__ void put_body(float4* a, const BodyF& s, F3 tail) const {
         const int t = threadIdx.x;
-        a[0 * NT + t] = s.x.x; a[1 * NT + t] = s.x.y; a[2 * NT + t] = s.x.z;
-        a[3 * NT + t] = s.r.x; a[4 * NT + t] = s.r.y; a[5 * NT + t] = s.r.z; a[6 * NT + t] = s.r.w;
-        a[7 * NT + t] = s.w.x; a[8 * NT + t] = s.w.y; a[9 * NT + t] = s.w.z;
-        a[10 * NT + t] = s.v.x; a[11 * NT + t] = s.v.y; a[12 * NT + t] = s.v.z;
+        a[0 * NT + t] = make_float4(s.x.x, s.x.y, s.x.z, s.r.x);
+        a[1 * NT + t] = make_float4(s.r.y, s.r.z, s.r.w, s.w.x);
+        a[2 * NT + t] = make_float4(s.w.y, s.w.z, s.v.x, s.v.y);
+        a[3 * NT + t] = make_float4(s.v.z, tail.x, tail.y, tail.z);
     }
-    __device__ __forceinline__ BodyF get_body(const float* a, int t) const {
+    __device__ __forceinline__ BodyF get_body(const float4* a, int t, F3& tail) const {
+        const float4 q0 = a[0 * NT + t], q1 = a[1 * NT + t], q2 = a[2 * NT + t], q3 = a[3 * NT + t];
         BodyF o;
-        o.x = v3<float>(a[0 * NT + t], a[1 * NT + t], a[2 * NT + t]);
-        o.r = q4<float>(a[3 * NT + t], a[4 * NT + t], a[5 * NT + t], a[6 * NT + t]);
-        o.w = v3<float>(a[7 * NT + t], a[8 * NT + t], a[9 * NT + t]);
-        o.v = v3<float>(a[10 * NT + t], a[11 * NT + t], a[12 * NT + t]);
+        o.x = v3<float>(q0.x, q0.y, q0.z);
+        o.r = q4<float>(q0.w, q1.x, q1.y, q1.z);
+        o.w = v3<float>(q1.w, q2.x, q2.y);
+        o.v = v3<float>(q2.z, q2.w, q3.x);
+        tail = v3<float>(q3.y, q3.z, q3.w);
         return o;
     }
+    __device__ __forceinline__ void put_wrench(float4* a, const WrenchF& w) const {
+        const int t = threadIdx.x;
+        a[0 * NT + t] = make_float4(w.t.x, w.t.y, w.t.z, w.f.x);
+        *(float2*)&a[1 * NT + t] = make_float2(w.f.y, w.f.z);
+    }
+    __device__ __forceinline__ WrenchF get_wrench(const float4* a, int t) const {
+        const float4 q0 = a[0 * NT + t];
+        const float2 q1 = *(const float2*)&a[1 * NT + t];
+        WrenchF w;
+        w.t = v3<float>(q0.x, q0.y, q0.z);
+        w.f = v3<float>(q0.w, q1.x, q1.y);
+        return w;
+    }
     __device__ __forceinline__ BodyF parent_body(const BodyF& s, int ps) const {
-        put_body(ex, s);
+        F3 tail;
+        put_body(ex, s, vzero<float>());
         __syncthreads();
-        BodyF o = get_body(ex, ps);
+        BodyF o = get_body(ex, ps, tail);
         __syncthreads();
         return o;
     }
     __device__ __forceinline__ F3 parent_vec(F3 v, int ps) const {
-        const int t = threadIdx.x;
-        ex[0 * NT + t] = v.x; ex[1 * NT + t] = v.y; ex[2 * NT + t] = v.z;
+        ex[threadIdx.x] = make_float4(v.x, v.y, v.z, 0.f);
         __syncthreads();
-        F3 o = v3<float>(ex[0 * NT + ps], ex[1 * NT + ps], ex[2 * NT + ps]);
+        const float4 q = ex[ps];
         __syncthreads();
-        return o;
+        return v3<float>(q.x, q.y, q.z);
     }
     // ---- split phase: in the substep loops a post_state* / get_parent_state* pair (area `ex`, barrier A) always
     // alternates with a post_* / gather_* pair (area `msg`, barrier B); a thread can only pass wait(B) of substep t
     // after every thread has arrived at B, i.e. after it finished reading `ex` of substep t, and vice versa.
     __device__ __forceinline__ void post_state(const BodyF& s, F3 xc) {
-        const int t = threadIdx.x;
-        put_body(ex, s);
-        ex[13 * NT + t] = xc.x; ex[14 * NT + t] = xc.y; ex[15 * NT + t] = xc.z;
+        put_body(ex, s, xc);
         mbar_arrive(bar);
     }
     __device__ __forceinline__ void post_state_w(const BodyF& s, F3 xc, const WrenchF& w) {
-        const int t = threadIdx.x;
-        put_body(ex, s);
-        ex[13 * NT + t] = xc.x; ex[14 * NT + t] = xc.y; ex[15 * NT + t] = xc.z;
-        ex[16 * NT + t] = w.t.x; ex[17 * NT + t] = w.t.y; ex[18 * NT + t] = w.t.z;
-        ex[19 * NT + t] = w.f.x; ex[20 * NT + t] = w.f.y; ex[21 * NT + t] = w.f.z;
+        put_body(ex, s, xc);
+        put_wrench(ex + 4 * NT, w);
         mbar_arrive(bar);
     }
     __device__ __forceinline__ void get_parent_state(const BodyF&, F3, int ps, BodyF& P, F3& xcp) {
         mbar_wait(bar, phA); phA ^= 1u;
-        P = get_body(ex, ps);
-        xcp = v3<float>(ex[13 * NT + ps], ex[14 * NT + ps], ex[15 * NT + ps]);
+        P = get_body(ex, ps, xcp);
     }
     __device__ __forceinline__ void get_parent_state_w(const BodyF&, F3, const WrenchF&, int ps, BodyF& P, F3& xcp,
                                                        WrenchF& wp) {
         mbar_wait(bar, phA); phA ^= 1u;
-        P = get_body(ex, ps);
-        xcp = v3<float>(ex[13 * NT + ps], ex[14 * NT + ps], ex[15 * NT + ps]);
-        wp.t = v3<float>(ex[16 * NT + ps], ex[17 * NT + ps], ex[18 * NT + ps]);
-        wp.f = v3<float>(ex[19 * NT + ps], ex[20 * NT + ps], ex[21 * NT + ps]);
+        P = get_body(ex, ps, xcp);
+        wp = get_wrench(ex + 4 * NT, ps);
     }
     __device__ __forceinline__ void post_wrench(const WrenchF& mine) {
-        const int t = threadIdx.x;
-        msg[0 * NT + t] = mine.t.x; msg[1 * NT + t] = mine.t.y; msg[2 * NT + t] = mine.t.z;
-        msg[3 * NT + t] = mine.f.x; msg[4 * NT + t] = mine.f.y; msg[5 * NT + t] = mine.f.z;
+        put_wrench(msg, mine);
         mbar_arrive(bar + 1);
     }
     __device__ __forceinline__ void post_body(const BodyF& mine) {
-        put_body(msg, mine);
+        put_body(msg, mine, vzero<float>());
         mbar_arrive(bar + 1);
     }
     __device__ __forceinline__ void gather_wrench(const WrenchF&, unsigned long long child, int maxc, WrenchF& acc) {
@@ -289,29 +307,30 @@ template <int NT> struct BlockComm {
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
             if (c) {
-                c += threadIdx.x;
-                acc.t += v3<float>(msg[0 * NT + c], msg[1 * NT + c], msg[2 * NT + c]);
-                acc.f += v3<float>(msg[3 * NT + c], msg[4 * NT + c], msg[5 * NT + c]);
+                const WrenchF w = get_wrench(msg, (int)(threadIdx.x + c));
+                acc.t += w.t; acc.f += w.f;
             }
         }
     }
     __device__ __forceinline__ void gather_body(const BodyF&, unsigned long long child, int maxc, BodyF& acc) {
         mbar_wait(bar + 1, phB); phB ^= 1u;
+        F3 tail;
 #pragma unroll 1
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
-            if (c) body_acc(acc, get_body(msg, (int)(threadIdx.x + c)));
+            if (c) body_acc(acc, get_body(msg, (int)(threadIdx.x + c), tail));
         }
     }
     // plain-barrier variant for the FK adjoint (outside the substep loop)
     __device__ __forceinline__ void gather_body_sync(const BodyF& mine, unsigned long long child, int maxc,
                                                      BodyF& acc) const {
-        put_body(msg, mine);
+        F3 tail;
+        put_body(msg, mine, vzero<float>());
         __syncthreads();
 #pragma unroll 1
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
-            if (c) body_acc(acc, get_body(msg, (int)(threadIdx.x + c)));
+            if (c) body_acc(acc, get_body(msg, (int)(threadIdx.x + c), tail));
         }
         __syncthreads();
     }
@@ -769,6 +788,7 @@ template <class Comm, bool ADJ> struct SmemLayout {
     static constexpr int comm = clist + NW * 32 * PPR_CLIST_STRIDE;
     static constexpr int total = comm + Comm::kExFloats;
     static constexpr size_t bytes = (size_t)total * sizeof(float);
+    static_assert(comm % 4 == 0, "exchange area must be 16-byte aligned");
 };
 
 template <class Comm, int JM, bool LIMITS, bool QOFF>
@@ -816,9 +836,12 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
 
     float* ck = A.ckpt + (warp * PPR_CKPT_FLOATS) * 32 + lane;
     const int64_t ck_step = A.nwarps * PPR_CKPT_FLOATS * 32;
+    // frame / checkpoint phases are carried as counters (no 64-bit divisions inside the time loop)
+    int64_t fi = -1, fphase = 0, kphase = 0;
     for (int64_t t = 0; t < A.nsteps; ++t) {
-        bool frame = (t % A.stride) == 0;
-        int64_t fi = t / A.stride;
+        const bool frame = fphase == 0;
+        fi += frame ? 1 : 0;
+        if (++fphase == A.stride) fphase = 0;
         int64_t frow = (fi * A.bs + L.env) * M.nb + L.body;
         if (frame && L.valid) {
             float* o = A.out_pos + frow * 7;
@@ -840,8 +863,11 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
                     (frame && A.out_grf) ? A.out_grf + frow * 6 : nullptr,
                     (frame && A.out_jaf) ? A.out_jaf + frow * 6 : nullptr, F, rec, ang);
         // checkpoint (coalesced: component-major rows of 32 lanes), every K-th substep
-        if (t % A.ckpt_every == 0) {
-        float* c = ck + (t / A.ckpt_every) * ck_step;
+        const bool keep = kphase == 0;
+        if (++kphase == A.ckpt_every) kphase = 0;
+        if (keep) {
+        float* c = ck;
+        ck += ck_step;
         c[0 * 32] = s.x.x; c[1 * 32] = s.x.y; c[2 * 32] = s.x.z;
         c[3 * 32] = s.r.x; c[4 * 32] = s.r.y; c[5 * 32] = s.r.z; c[6 * 32] = s.r.w;
         c[7 * 32] = s.w.x; c[8 * 32] = s.w.y; c[9 * 32] = s.w.z;
@@ -935,10 +961,14 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
             for (int k = 0; k < 6; ++k) r[k] = 0.f;
         }
     }
+    int64_t fi = last / A.stride, fphase = last % A.stride;   // frame index / phase of substep t, counted down
     for (int64_t t = last; t >= 0; --t) {
         // seed from the loss at frame steps
-        if ((t % A.stride) == 0 && L.valid) {
-            int64_t frow = ((t / A.stride) * A.bs + L.env) * M.nb + L.body;
+        const bool frame = fphase == 0;
+        const int64_t fcur = fi;
+        if (frame) { fphase = A.stride - 1; --fi; } else --fphase;
+        if (frame && L.valid) {
+            int64_t frow = (fcur * A.bs + L.env) * M.nb + L.body;
             const float* a = A.adj_pos + frow * 7;
             const float* b = A.adj_vel + frow * 6;
             adjN.x += v3<float>(a[0], a[1], a[2]);

@@ -63,7 +63,7 @@ def main():
     nw = float(os.environ.get("WARP_STEPS", "0"))
     print("total executed warp-instructions %.4g%s" % (tot, ("  = %.1f per warp-substep" % (tot / nw)) if nw else ""))
     ts = sum(smp.values()) or 1
-    for k, v in agg.most_common(60):
+    for k, v in agg.most_common(int(os.environ.get("TOP", "60"))):
         print("%6.2f%% inst %6.2f%% samples %s  %s" % (100 * v / tot, 100 * smp[k] / ts,
                                                       ("%7.1f/step" % (v / nw)) if nw else "", k))
 
