@@ -40,6 +40,9 @@ typedef M3<float> M3F;
 #define PPR_BLOCK 128  // FK kernels (warp layout)
 #define PPR_CLIST_CAP 16  // penetrating points listed per body before falling back to the cooperative path
 #define PPR_CLIST_STRIDE (PPR_CLIST_CAP + 1)
+#ifndef PPR_BODY_MAJOR
+#define PPR_BODY_MAJOR 1
+#endif
 #define FULL 0xffffffffu
 
 static std::atomic<int64_t> g_launches{0};
@@ -271,9 +274,11 @@ template <int NT> struct BlockComm {
         __syncthreads();
         return v3<float>(q.x, q.y, q.z);
     }
-    // ---- split phase: in the substep loops a post_state* / get_parent_state* pair (area `ex`, barrier A) always
-    // alternates with a post_* / gather_* pair (area `msg`, barrier B); a thread can only pass wait(B) of substep t
-    // after every thread has arrived at B, i.e. after it finished reading `ex` of substep t, and vice versa.
+    // ---- in the substep loops a post_state* / get_parent_state* pair (area `ex`, barrier A: split-phase mbarrier,
+    // the contact pass runs between arrive and wait) always alternates with a post_* / gather_* pair (area `msg`,
+    // barrier B: nothing to overlap, a plain hardware barrier that costs no polling issue slots); a thread can only
+    // pass B of substep t after every thread has reached B, i.e. after it finished reading `ex` of substep t, and
+    // can only pass wait(A) of t+1 after every thread arrived at A, i.e. finished reading `msg` of t.
     __device__ __forceinline__ void post_state(const BodyF& s, F3 xc) {
         put_body(ex, s, xc);
         mbar_arrive(bar);
@@ -293,16 +298,23 @@ template <int NT> struct BlockComm {
         P = get_body(ex, ps, xcp);
         wp = get_wrench(ex + 4 * NT, ps);
     }
+#ifdef PPR_MBAR_B   // barrier B as an mbarrier too (measured: its wait has no work to hide behind and only polls)
+#define PPR_ARRIVE_B() mbar_arrive(bar + 1)
+#define PPR_WAIT_B() do { mbar_wait(bar + 1, phB); phB ^= 1u; } while (0)
+#else
+#define PPR_ARRIVE_B()
+#define PPR_WAIT_B() __syncthreads()
+#endif
     __device__ __forceinline__ void post_wrench(const WrenchF& mine) {
         put_wrench(msg, mine);
-        mbar_arrive(bar + 1);
+        PPR_ARRIVE_B();
     }
     __device__ __forceinline__ void post_body(const BodyF& mine) {
         put_body(msg, mine, vzero<float>());
-        mbar_arrive(bar + 1);
+        PPR_ARRIVE_B();
     }
     __device__ __forceinline__ void gather_wrench(const WrenchF&, unsigned long long child, int maxc, WrenchF& acc) {
-        mbar_wait(bar + 1, phB); phB ^= 1u;
+        PPR_WAIT_B();
 #pragma unroll 1
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
@@ -313,7 +325,7 @@ template <int NT> struct BlockComm {
         }
     }
     __device__ __forceinline__ void gather_body(const BodyF&, unsigned long long child, int maxc, BodyF& acc) {
-        mbar_wait(bar + 1, phB); phB ^= 1u;
+        PPR_WAIT_B();
         F3 tail;
 #pragma unroll 1
         for (int sl = 0; sl < maxc; ++sl) {
@@ -357,24 +369,31 @@ struct LaneInfo {
 };
 
 // group = warp or block index, slot = lane or thread index inside it, epg = environments per group
-__device__ __forceinline__ LaneInfo lane_setup(const DevModel& M, int64_t group, int slot, int64_t n_env, int epg) {
+// body_major = false: slot = env_in_group * nb + body (a warp holds whole environments: what the shuffle exchange needs)
+// body_major = true : slot = body * epg + env_in_group (block layout): the lanes of a warp hold the SAME few bodies of
+//   all the group's environments, so joint-type / has-parent / has-children branches and the child-gather loops are
+//   (nearly) warp-uniform instead of every warp paying for the root's four children.
+__device__ __forceinline__ LaneInfo lane_setup(const DevModel& M, int64_t group, int slot, int64_t n_env, int epg,
+                                               bool body_major = false) {
     LaneInfo L;
     const int lane = slot;
-    int e_in_w = slot / M.nb;
-    int body = slot - e_in_w * M.nb;
+    int e_in_w, body;
+    if (body_major) { body = slot / epg; e_in_w = slot - body * epg; }
+    else { e_in_w = slot / M.nb; body = slot - e_in_w * M.nb; }
     int64_t env = group * epg + e_in_w;
-    L.valid = (e_in_w < epg) && (env < n_env);
+    L.valid = (e_in_w < epg) && (body < M.nb) && (env < n_env);
     if (!L.valid) { e_in_w = 0; body = 0; env = group * epg; }
-    int seg = e_in_w * M.nb;
+    const int sstride = body_major ? epg : 1;               // slot distance of consecutive bodies of one environment
+    const int seg = body_major ? e_in_w : e_in_w * M.nb;    // slot of body 0 of this environment
     L.env = (int)env; L.body = body;
     int4 ji = M.jinfo[body], j2 = M.jinfo2[body];
-    L.type = ji.x; L.has_parent = ji.y >= 0; L.parent_slot = L.has_parent ? seg + ji.y : lane;
+    L.type = ji.x; L.has_parent = ji.y >= 0; L.parent_slot = L.has_parent ? seg + ji.y * sstride : lane;
     L.qs = ji.z; L.qds = ji.w; L.ndof = j2.x; L.depth = j2.y; L.c0 = j2.z; L.c1 = j2.w;
     unsigned long long ch = M.child[body], out = 0;
 #pragma unroll
     for (int s = 0; s < PPR_MAX_CHILD; ++s) {
         unsigned c = (unsigned)((ch >> (8 * s)) & 0xffu);
-        unsigned long long v = (c == 0xffu || !L.valid) ? 0ull : (unsigned long long)(c - (unsigned)body);
+        unsigned long long v = (c == 0xffu || !L.valid) ? 0ull : (unsigned long long)((c - (unsigned)body) * sstride);
         out |= v << (8 * s);
     }
     L.child = out;
@@ -808,7 +827,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     comm.init();
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
     if (M.nc > 0) cm0 = load_mat(M, 0);
-    LaneInfo L = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M));
+    LaneInfo L = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M), Comm::kBlock && PPR_BODY_MAJOR);
     // per-env parameters of this body / joint -> shared memory
     int64_t ebp = (int64_t)L.env * A.pstride * M.nb + L.body;
     par[0] = A.inv_m[ebp];
@@ -913,7 +932,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     comm.init();
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
     if (M.nc > 0) cm0 = load_mat(M, 0);
-    LaneInfo L = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M));
+    LaneInfo L = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M), Comm::kBlock && PPR_BODY_MAJOR);
     int64_t eb = (int64_t)L.env * M.nb + L.body;
     int64_t ebp = (int64_t)L.env * A.pstride * M.nb + L.body;
     par[0] = A.inv_m[ebp];
@@ -1124,7 +1143,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     {
         float jq[7], jqd[6];
         comm.sync();
-        LaneInfo L2 = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M));  // re-derived (was in smem)
+        LaneInfo L2 = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M), Comm::kBlock && PPR_BODY_MAJOR);  // re-derived (was in smem)
         load_joint_coords(L2, A.q_init, A.qd_init, M.nq, M.nqd, jq, jqd);
         BodyF s0 = warp_fk<JM>(comm, M, L2, jq, jqd);
         warp_fk_adjoint<JM>(comm, M, L2, s0, adjN, jq, jqd, A.adj_q_init, A.adj_qd_init);

@@ -38,7 +38,11 @@ def main():
     nwarps = ngroups * (threads // 32)
     rows = ws[: (T - 1) * nwarps * 28 * 32].view(T - 1, nwarps, 28, 32)
     cnt = rows[:, :, 19, :].contiguous().view(torch.int32).cpu().numpy()          # T-1, nwarps, 32
-    cnt = cnt.reshape(T - 1, ngroups, threads)[:, :, : epg * rm.nb].reshape(T - 1, ngroups, epg, rm.nb)
+    cnt = cnt.reshape(T - 1, ngroups, threads)[:, :, : epg * rm.nb]
+    if threads > 32:   # block layout: slot = body * epg + env_in_group
+        cnt = cnt.reshape(T - 1, ngroups, rm.nb, epg).transpose(0, 1, 3, 2)
+    else:              # warp layout: slot = env_in_group * nb + body
+        cnt = cnt.reshape(T - 1, ngroups, epg, rm.nb)
     print("workload %s, %d envs, packing %d threads / %d envs" % (wl, bs, threads, epg))
     print("mean active points per env-substep: %.2f" % cnt.sum(-1).mean())
     print("per body mean:", np.round(cnt.mean((0, 1, 2)), 2))
