@@ -356,11 +356,12 @@ template <int NT> struct BlockComm {
 // Reads go through volatile pointers so that ptxas re-issues the (29-cycle) LDS at the point of use instead of
 // hoisting the values back into loop-long registers.
 #define PPR_NSTATIC 28  // xpj 3, qpj 4, axis 3, com 3, parent com 3, aabb 7, qoff 4, pad 1
-#define PPR_NPAR 19
+#define PPR_NPAR 20
 enum { ST_XPJ = 0, ST_QPJ = 3, ST_AXIS = 7, ST_COM = 10, ST_CPAR = 13, ST_AABB = 16, ST_QOFF = 23 };
 
 struct LaneInfo {
     int env, body, parent_slot, type, ndof, depth, qs, qds, c0, c1;
+    int maxc_w;  // largest child count among the lanes of this WARP (trip count of the child-gather loops)
     bool valid, has_parent;
     unsigned long long child;  // children as byte offsets from the own slot (child body index - own body index), 0 none
     JointStatic<float> js;
@@ -397,6 +398,10 @@ __device__ __forceinline__ LaneInfo lane_setup(const DevModel& M, int64_t group,
         out |= v << (8 * s);
     }
     L.child = out;
+    int nchild = 0;
+#pragma unroll
+    for (int s = 0; s < PPR_MAX_CHILD; ++s) if ((out >> (8 * s)) & 0xffull) nchild = s + 1;
+    L.maxc_w = __reduce_max_sync(FULL, nchild);
     const float* xp = M.xpj + 7 * body;
     L.js.type = L.type;
     L.js.xpj = v3<float>(xp[0], xp[1], xp[2]);
@@ -438,10 +443,29 @@ __device__ __forceinline__ JointStatic<float> st_joint(const volatile float* st,
                    : q4<float>(0.f, 0.f, 0.f, 1.f);
     return js;
 }
+// per-thread parameters as five float4 quads [5][NT]: (inv_m, I0..I2) (I3..I6) (I7, I8, J0, J1) (J2..J5) (J6..J8, -);
+// `asm volatile` loads: re-issued at the point of use in every substep, never hoisted into loop-long registers
+__device__ __forceinline__ float4 lds128v(const float4* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
 template <int NT>
-__device__ __forceinline__ void par_load9(const volatile float* par, int row0, float* out) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) out[i] = par[(row0 + i) * NT];
+__device__ __forceinline__ void par_store(float4* par, float inv_m, const float* I, const float* J) {
+    par[0 * NT] = make_float4(inv_m, I[0], I[1], I[2]);
+    par[1 * NT] = make_float4(I[3], I[4], I[5], I[6]);
+    par[2 * NT] = make_float4(I[7], I[8], J[0], J[1]);
+    par[3 * NT] = make_float4(J[2], J[3], J[4], J[5]);
+    par[4 * NT] = make_float4(J[6], J[7], J[8], 0.f);
+}
+template <int NT>
+__device__ __forceinline__ void par_load(const float4* par, float& inv_m, float* I, float* J) {
+    const float4 a = lds128v(par), b = lds128v(par + NT), c = lds128v(par + 2 * NT), d = lds128v(par + 3 * NT),
+                 e = lds128v(par + 4 * NT);
+    inv_m = a.x;
+    I[0] = a.y; I[1] = a.z; I[2] = a.w; I[3] = b.x; I[4] = b.y; I[5] = b.z; I[6] = b.w; I[7] = c.x; I[8] = c.y;
+    J[0] = c.z; J[1] = c.w; J[2] = d.x; J[3] = d.y; J[4] = d.z; J[5] = d.w; J[6] = e.x; J[7] = e.y; J[8] = e.z;
 }
 
 __device__ __forceinline__ ContactMat<float> load_mat(const DevModel& M, int k) {
@@ -784,7 +808,7 @@ __device__ __forceinline__ void warp_forces(Comm& comm, const DevModel& M, const
         if (L.has_parent) { Wp.t = t + cross(ap, f); Wp.f = f; }
     }
     comm.post_wrench(Wp);
-    comm.gather_wrench(Wp, L.child, M.maxc, F);
+    comm.gather_wrench(Wp, L.child, L.maxc_w, F);
     if (jaf_row && L.valid) {
         WrenchF J; J.t = F.t - G.t; J.f = F.f - G.f;
         store_wrench_row(jaf_row, J);
@@ -803,11 +827,11 @@ template <class Comm, bool ADJ> struct SmemLayout {
     static constexpr int st = row + (ADJ ? NW * PPR_CKPT_FLOATS * 32 : 0);
     static constexpr int par = st + PPR_NSTATIC * 32;
     static constexpr int acc = par + PPR_NPAR * NT;
-    static constexpr int clist = acc + (ADJ ? 18 * NT : 0);
+    static constexpr int clist = acc + (ADJ ? 20 * NT : 0);
     static constexpr int comm = clist + NW * 32 * PPR_CLIST_STRIDE;
     static constexpr int total = comm + Comm::kExFloats;
     static constexpr size_t bytes = (size_t)total * sizeof(float);
-    static_assert(comm % 4 == 0, "exchange area must be 16-byte aligned");
+    static_assert(comm % 4 == 0 && par % 4 == 0 && acc % 4 == 0, "float4 areas must be 16-byte aligned");
 };
 
 template <class Comm, int JM, bool LIMITS, bool QOFF>
@@ -822,7 +846,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     const int lane = threadIdx.x & 31;
     int* clist = (int*)(smem + SL::clist) + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
     volatile float* st = smem + SL::st;
-    volatile float* par = smem + SL::par + threadIdx.x;
+    float4* par = (float4*)(smem + SL::par) + threadIdx.x;
     if (group >= A.ngroups) return;
     comm.init();
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
@@ -830,9 +854,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     LaneInfo L = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M), Comm::kBlock && PPR_BODY_MAJOR);
     // per-env parameters of this body / joint -> shared memory
     int64_t ebp = (int64_t)L.env * A.pstride * M.nb + L.body;
-    par[0] = A.inv_m[ebp];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { par[(1 + i) * NT] = A.I[ebp * 9 + i]; par[(10 + i) * NT] = A.inv_I[ebp * 9 + i]; }
+    par_store<NT>(par, A.inv_m[ebp], A.I + ebp * 9, A.inv_I + ebp * 9);
     JointCtl<float> ctl;
     float ke[3], kd[3];
 #pragma unroll
@@ -900,10 +922,9 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         c[27 * 32] = 0.f;  // pad: the adjoint copies whole rows
         }
         {
-            float I[9], inv_I[9];
-            par_load9<NT>(par, 1, I);
-            par_load9<NT>(par, 10, inv_I);
-            s = integrate_fwd(s, Rb, xc, com, F, par[0], I, inv_I, g, A.dt);
+            float inv_m, I[9], inv_I[9];
+            par_load<NT>(par, inv_m, I, inv_I);
+            s = integrate_fwd(s, Rb, xc, com, F, inv_m, I, inv_I, g, A.dt);
         }
     }
 }
@@ -924,8 +945,8 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     const int lane = threadIdx.x & 31;
     int* clist = (int*)(smem + SL::clist) + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
     volatile float* st = smem + SL::st;
-    volatile float* par = smem + SL::par + threadIdx.x;
-    volatile float* acc = smem + SL::acc + threadIdx.x;
+    float4* par = (float4*)(smem + SL::par) + threadIdx.x;
+    float4* acc = (float4*)(smem + SL::acc) + threadIdx.x;
     volatile float* roww = smem + SL::row + (threadIdx.x >> 5) * PPR_CKPT_FLOATS * 32;  // this warp's row buffer
     volatile float* row = roww + (threadIdx.x & 31);
     if (group >= A.ngroups) return;
@@ -935,11 +956,9 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     LaneInfo L = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M), Comm::kBlock && PPR_BODY_MAJOR);
     int64_t eb = (int64_t)L.env * M.nb + L.body;
     int64_t ebp = (int64_t)L.env * A.pstride * M.nb + L.body;
-    par[0] = A.inv_m[ebp];
+    par_store<NT>(par, A.inv_m[ebp], A.I + ebp * 9, A.inv_I + ebp * 9);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { par[(1 + i) * NT] = A.I[ebp * 9 + i]; par[(10 + i) * NT] = A.inv_I[ebp * 9 + i]; }
-#pragma unroll
-    for (int i = 0; i < 18; ++i) acc[i * NT] = 0.f;
+    for (int i = 0; i < 5; ++i) acc[i * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
     JointCtl<float> ctl;
     float ke[3], kd[3];
     const bool jon = L.type != JT_FREE;
@@ -1030,10 +1049,9 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
                 c[24 * 32] = angr[0]; c[25 * 32] = angr[1]; c[26 * 32] = angr[2];
                 c[27 * 32] = 0.f;
                 if (tr < tp) {
-                    float I[9], inv_I[9];
-                    par_load9<NT>(par, 1, I);
-                    par_load9<NT>(par, 10, inv_I);
-                    sr = integrate_fwd(sr, Rr, xcr, comr, Fr, par[0], I, inv_I, g, A.dt);
+                    float inv_m, I[9], inv_I[9];
+                    par_load<NT>(par, inv_m, I, inv_I);
+                    sr = integrate_fwd(sr, Rr, xcr, comr, Fr, inv_m, I, inv_I, g, A.dt);
                 }
             }
             __threadfence_block();
@@ -1079,21 +1097,19 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         F3 adj_xc = vzero<float>();
         WrenchF adjF;
         {
-            float I[9], inv_I[9];
-            par_load9<NT>(par, 1, I);
-            par_load9<NT>(par, 10, inv_I);
+            float inv_m, I[9], inv_I[9];
+            par_load<NT>(par, inv_m, I, inv_I);
             F3 ga, gb, gc, gd;
-            integrate_adj_core(s, Rb, xc, com, F, par[0], I, inv_I, g, A.dt, adjN, adjS, G, adj_xc, adjF, a_inv_m, ga,
+            integrate_adj_core(s, Rb, xc, com, F, inv_m, I, inv_I, g, A.dt, adjN, adjS, G, adj_xc, adjF, a_inv_m, ga,
                                gb, gc, gd);
-            const float av[3] = {ga.x, ga.y, ga.z}, bv[3] = {gb.x, gb.y, gb.z};
-            const float cv[3] = {gc.x, gc.y, gc.z}, dv[3] = {gd.x, gd.y, gd.z};
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    acc[(3 * i + j) * NT] += av[i] * bv[j];
-                    acc[(9 + 3 * i + j) * NT] += cv[i] * dv[j];
-                }
+            // adj_I += ga gb^T, adj_inv_I += gc gd^T: 18 accumulators as five float4 quads in shared memory
+            float4 q0 = acc[0 * NT], q1 = acc[1 * NT], q2 = acc[2 * NT], q3 = acc[3 * NT], q4 = acc[4 * NT];
+            q0.x += ga.x * gb.x; q0.y += ga.x * gb.y; q0.z += ga.x * gb.z; q0.w += ga.y * gb.x;
+            q1.x += ga.y * gb.y; q1.y += ga.y * gb.z; q1.z += ga.z * gb.x; q1.w += ga.z * gb.y;
+            q2.x += ga.z * gb.z; q2.y += gc.x * gd.x; q2.z += gc.x * gd.y; q2.w += gc.x * gd.z;
+            q3.x += gc.y * gd.x; q3.y += gc.y * gd.y; q3.z += gc.y * gd.z; q3.w += gc.z * gd.x;
+            q4.x += gc.z * gd.y; q4.y += gc.z * gd.z;
+            acc[0 * NT] = q0; acc[1 * NT] = q1; acc[2 * NT] = q2; acc[3 * NT] = q3; acc[4 * NT] = q4;
         }
         comm.post_state_w(s, xc, adjF);   // published before the contact replay, awaited after it
         // K3^T (needs only this body's adjF)
@@ -1132,7 +1148,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
                 if (A.adj_torques) A.adj_torques[row + k] = 0.f;
             }
         }
-        comm.gather_body(adjP, L.child, M.maxc, adjS);
+        comm.gather_body(adjP, L.child, L.maxc_w, adjS);
         // world COM -> pose
         adjS.x += adj_xc;
         m3_acc(G, adj_xc, com);
@@ -1151,7 +1167,10 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     if (L.valid) {
         A.adj_inv_m[eb] = nan0(a_inv_m);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) { A.adj_I[eb * 9 + i] = nan0(acc[i * NT]); A.adj_inv_I[eb * 9 + i] = nan0(acc[(9 + i) * NT]); }
+        for (int i = 0; i < 9; ++i) {
+            A.adj_I[eb * 9 + i] = nan0(((const float*)&acc[(i >> 2) * NT])[i & 3]);
+            A.adj_inv_I[eb * 9 + i] = nan0(((const float*)&acc[((9 + i) >> 2) * NT])[(9 + i) & 3]);
+        }
         int64_t d = (int64_t)L.env * M.nqd + L.qds;
 #pragma unroll
         for (int k = 0; k < 3; ++k) if (jon && k < L.ndof) { A.adj_ke[d + k] = nan0(a_ke[k]); A.adj_kd[d + k] = nan0(a_kd[k]); }
