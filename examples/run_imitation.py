@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 
 import torch  # noqa: E402
 
-from ppr_diffphys_b200.imitation import ImitationModel  # noqa: E402
+from ppr_diffphys_b200.imitation import GraphedStep, ImitationModel  # noqa: E402
 
 
 def main():
@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--frames-per-wdw", type=int, default=24)
     ap.add_argument("--log-every", type=int, default=10)
     ap.add_argument("--lr", type=float, default=1e-4)
+    ap.add_argument("--no-graph", action="store_true", help="eager iterations instead of one CUDA-graph replay each")
     args = ap.parse_args()
     torch.manual_seed(8)
     model = ImitationModel(args.robot, args.seqname, total_iters=args.iters, lr=args.lr)
@@ -36,13 +37,17 @@ def main():
     model.reinit_envs(args.num_envs, args.frames_per_wdw)
     T = len(model.steps_idx)
     losses, times = [], []
+    step = None if args.no_graph else GraphedStep(model)
     for it in range(args.iters):
         model.progress = it / max(1, args.iters - 1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        loss_dict = model()
-        model.backward(loss_dict["total_loss"])
-        info = model.update()
+        if step is not None:
+            loss_dict, info = step()
+        else:
+            loss_dict = model()
+            model.backward(loss_dict["total_loss"])
+            info = model.update()
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
         losses.append(float(loss_dict["loss_traj"].detach()))
@@ -54,7 +59,7 @@ def main():
     med = steady[len(steady) // 2]
     print(json.dumps({"robot": args.robot, "seqname": args.seqname, "iters": args.iters, "num_envs": args.num_envs,
                       "substeps": T, "loss_traj_first": sum(losses[:k]) / k, "loss_traj_last": sum(losses[-k:]) / k,
-                      "median_iter_ms": med * 1e3, "env_steps_per_sec": args.num_envs * (T - 1) / med}))
+                      "cuda_graph": step is not None, "median_iter_ms": med * 1e3, "env_steps_per_sec": args.num_envs * (T - 1) / med}))
 
 
 if __name__ == "__main__":

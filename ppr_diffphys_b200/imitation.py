@@ -70,9 +70,11 @@ def se3_loss(pred, gt, rot_ratio=0.1):
 
 
 def reduce_loss(loss_seq):
-    """dp_utils.py:93-110 without the trajectory clipping branch."""
+    """dp_utils.py:93-110 without the trajectory clipping branch: mean over the entries > 0 (all entries when none
+    is).  Written as a masked mean -- no boolean indexing, no host read -- so the step can be captured in a CUDA
+    graph; identical because the se3 losses are >= 0 (no entry > 0  <=>  every entry is 0  <=>  both means are 0)."""
     pos = loss_seq > 0
-    return loss_seq[pos].mean() if bool(pos.any()) else loss_seq.mean()
+    return torch.where(pos, loss_seq, torch.zeros_like(loss_seq)).sum() / pos.sum().clamp_min(1)
 
 
 def rotate_frame(global_q, q):
@@ -173,6 +175,7 @@ class ImitationModel(nn.Module):
         self.total_frames = frames.shape[0]
         self.steps_per_fr_interval = int(self.frame_interval / self.dt)
         self.register_buffer("amp_info", torch.as_tensor(frames))
+        self.register_buffer("bullet2gl", _BULLET2GL.clone(), persistent=False)
 
     def get_mocap_data(self, steps_fr):
         """linear interpolation / extrapolation of all columns at fractional frame ids (dp_model.py:421-427),
@@ -181,7 +184,7 @@ class ImitationModel(nn.Module):
         w = (steps_fr - f0.float())[..., None]
         amp = self.amp_info[f0] * (1 - w) + self.amp_info[f0 + 1] * w
         m = parse_amp(amp)
-        P = _BULLET2GL.to(amp.device)
+        P = self.bullet2gl
         out = dict(jang=m["jang"], jvel=m["jvel"])
         out["pos"] = m["pos"] @ P.T
         out["orn"] = torch.cat([m["orn"][..., :3] @ P.T, m["orn"][..., 3:]], -1)
@@ -215,9 +218,12 @@ class ImitationModel(nn.Module):
         self.frame2step = [i for i in self.steps_idx if i % spf == 0]
         self.is_eval = is_eval
 
-    def compute_frame_start(self):
+    def compute_frame_start_host(self):
         fs = self.rng.rand(self.num_envs) * (self.total_frames - self.frames_per_wdw)
-        return torch.as_tensor(np.round(fs), device=self.device, dtype=torch.float32)
+        return torch.as_tensor(np.round(fs), dtype=torch.float32)
+
+    def compute_frame_start(self):
+        return self.compute_frame_start_host().to(self.device)
 
     def fk_pos_vel(self, q, ja, qd, jad):
         """(bs,F,..) targets -> body poses / twists through ForwardKinematics (dp_model.py:588-603)."""
@@ -230,7 +236,7 @@ class ImitationModel(nn.Module):
         msm = self.get_mocap_data(steps_fr)
         target_q = rotate_frame(self.global_q, torch.cat([msm["pos"], msm["orn"]], -1))      # bs,T,7
         target_qd = rotate_frame_vel(self.global_q, torch.cat([msm["vel"], msm["avel"]], -1))  # bs,T,6
-        f2s = self.frame2step
+        f2s = slice(0, None, self.steps_per_fr_interval)   # == self.frame2step (evenly strided), as a view: no index tensor
         target_position, _, self.target_trajs = self.fk_pos_vel(target_q[:, f2s], msm["jang"][:, f2s],
                                                                 target_qd[:, f2s], msm["jvel"][:, f2s])
         fid = steps_fr.reshape(-1)
@@ -247,19 +253,31 @@ class ImitationModel(nn.Module):
         return target_position, ref_ja, q_all, qd_all
 
     # ---- one optimisation step -------------------------------------------------------------------------
-    def forward(self, frame_start=None):
+    def draw_noise(self):
+        """initial-state noise of a training iteration (dp_model.py:700-712), drawn on the host like the reference;
+        None when the iteration adds none (eval)."""
+        if not (self.training and self.noise_std > 0 and not self.is_eval):
+            return None
+        ratio = float(np.clip(1 - 1.5 * self.progress, 0, 1))
+        noise = torch.as_tensor(self.rng.normal(size=(self.num_envs, self.env.nq), scale=self.noise_std * ratio),
+                                dtype=torch.float32)
+        noise[:, :3] = 0
+        noise[:, 3:7] *= 5
+        return noise
+
+    def forward(self, frame_start=None, noise=None):
+        """``noise``: [bs, nq] tensor added to q_init (GraphedStep passes a static buffer); None = draw it here."""
         if frame_start is None:
             frame_start = self.compute_frame_start()
+        if noise is None:
+            noise = self.draw_noise()
+            if noise is not None:
+                noise = noise.to(self.device)
         steps_fr = frame_start[:, None] + self.steps_idx_fr[None]                     # bs,T
         target_position, ref_ja, queried_q, queried_qd = self.get_batch_input(steps_fr)
         bs, F = self.num_envs, self.frames_per_wdw
         q_init = queried_q[0].reshape(-1)
-        if self.training and self.noise_std > 0 and not self.is_eval:                 # dp_model.py:700-712
-            ratio = float(np.clip(1 - 1.5 * self.progress, 0, 1))
-            noise = torch.as_tensor(self.rng.normal(size=(bs, self.env.nq), scale=self.noise_std * ratio),
-                                    device=self.device, dtype=torch.float32)
-            noise[:, :3] = 0
-            noise[:, 3:7] *= 5
+        if noise is not None:
             q_init = q_init + noise.reshape(-1)
         qd_init = convert_ppr_warp(queried_qd[0].view(bs, -1)).reshape(-1)
         inv_m = 1.0 / self.body_mass
@@ -268,7 +286,7 @@ class ImitationModel(nn.Module):
         sim_position, sim_velocity = ForwardWarp.apply(q_init, qd_init, None, None, ref_ja, self.target_ke,
                                                        self.target_kd, self.body_mass, inv_m, I, inv_I, self)
         sim_velocity = convert_ppr_warp(sim_velocity)
-        f2s = self.frame2step
+        f2s = slice(0, None, self.steps_per_fr_interval)
         qq = queried_q[f2s].reshape(F, bs, -1)
         qqd = convert_ppr_warp(queried_qd[f2s].reshape(F, bs, -1))
         queried_position, queried_velocity, self.pid_ref = ForwardKinematics.apply(qq, qqd, self.env)
@@ -288,12 +306,73 @@ class ImitationModel(nn.Module):
     def backward(self, loss):
         loss.backward()
 
-    def update(self, thresh=10.0):
+    def update(self, thresh=10.0, keep_grads=False):
+        """clip, sanity-check and apply the gradients (dp_model.py:511-548,936-963 without the roll-back): an
+        iteration whose gradient norm is non-finite or above ``thresh`` is skipped (the reference drops the gradients,
+        which makes its optimizer step a no-op).  ``keep_grads``: leave the .grad tensors in place (GraphedStep
+        re-fills the same memory on the next replay)."""
         params = [p for g in self.optimizer.param_groups for p in g["params"] if p.grad is not None]
         grad_norm = torch.nn.utils.clip_grad_norm_(params, thresh)
-        if not torch.isfinite(grad_norm) or grad_norm > thresh:   # check_grad (:936-963) without the roll-back
-            self.optimizer.zero_grad()
-        self.optimizer.step()
+        skipped = bool(not torch.isfinite(grad_norm) or grad_norm > thresh)
+        if not skipped:
+            self.optimizer.step()
         self.scheduler.step()
-        self.optimizer.zero_grad()
-        return {"grad_norm": float(grad_norm)}
+        if not keep_grads:
+            self.optimizer.zero_grad()
+        return {"grad_norm": float(grad_norm), "skipped": skipped}
+
+
+class GraphedStep:
+    """forward + losses + backward of one optimisation iteration captured ONCE in a CUDA graph and replayed.
+
+    The reference-shaped problem (10..64 windows x 760 substeps, dp_model.py:354-367) cannot fill a B200: an iteration
+    is a few hundred small launches (three MLPs, mocap interpolation, two FK calls, the rollout pair, se3 losses
+    and their backward) whose launch overhead, not their run time, sets the iteration time.  Everything that
+    changes between iterations enters through two static device buffers (window start frames, initial-state
+    noise), both drawn on the host exactly like the eager path, so the two paths consume the same random stream.
+    The optimizer step stays eager: its skip decision needs the gradient norm on the host (as in the reference).
+
+        step = GraphedStep(model)           # after model.train(); model.reinit_envs(...)
+        for it in range(iters):
+            model.progress = it / (iters - 1)
+            out, info = step()              # out: dict of static loss tensors, info: update() result
+    """
+
+    def __init__(self, model, warmup=3):
+        self.model = m = model
+        dev = m.device
+        self.frame_start = torch.zeros(m.num_envs, device=dev)
+        self.noise = torch.zeros(m.num_envs, m.env.nq, device=dev)
+        self._h_frame_start = torch.zeros(m.num_envs).pin_memory()
+        self._h_noise = torch.zeros(m.num_envs, m.env.nq).pin_memory()
+        m.optimizer.zero_grad(set_to_none=True)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):       # warm-up off the default stream (allocator pools, lazy kernel attributes)
+            for _ in range(warmup):
+                out = m(frame_start=self.frame_start, noise=self.noise)
+                out["total_loss"].backward()
+                m.optimizer.zero_grad(set_to_none=True)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = m(frame_start=self.frame_start, noise=self.noise)
+            self.out["total_loss"].backward()
+        self.launches_per_replay = None
+
+    def __call__(self, frame_start=None, thresh=10.0):
+        m = self.model
+        if frame_start is None:
+            self._h_frame_start.copy_(m.compute_frame_start_host())
+            self.frame_start.copy_(self._h_frame_start, non_blocking=True)
+        else:
+            self.frame_start.copy_(torch.as_tensor(frame_start, dtype=torch.float32), non_blocking=True)
+        noise = m.draw_noise()
+        if noise is None:
+            self.noise.zero_()
+        else:
+            self._h_noise.copy_(noise)
+            self.noise.copy_(self._h_noise, non_blocking=True)
+        self.graph.replay()
+        info = m.update(thresh, keep_grads=True)
+        return self.out, info

@@ -47,3 +47,35 @@ def test_eval_rollout_side_channels():
     assert len(model.steps_idx) == 33 * (F - 1) + 1
     assert len(model.grfs) == F and model.grfs[0].shape == (13, 6) and len(model.sim_trajs) == F
     assert model.sim_trajs[0].shape == (13, 7) and torch.isfinite(out["total_loss"])
+
+
+def test_graphed_step_matches_eager_iterations():
+    """One CUDA-graph replay per iteration (GraphedStep) == the eager forward / backward / update sequence: same
+    random stream, same losses and the same parameters after a few iterations."""
+    from ppr_diffphys_b200.imitation import GraphedStep, ImitationModel
+
+    def run(graphed, iters=6):
+        torch.manual_seed(8)
+        model = ImitationModel("laikago", "mi-trot", total_iters=iters, lr=1e-4, seed=3)
+        model.record_forces = False
+        model.train()
+        model.reinit_envs(6, 5)
+        step = GraphedStep(model) if graphed else None
+        losses = []
+        for it in range(iters):
+            model.progress = it / iters
+            if graphed:
+                out, info = step()
+            else:
+                out = model()
+                model.backward(out["total_loss"])
+                info = model.update()
+            assert not info["skipped"]
+            losses.append([float(out[k].detach()) for k in ("loss_traj", "loss_pos_state", "loss_vel_state")])
+        return torch.tensor(losses), [p.detach().clone() for p in model.parameters()]
+
+    l0, p0 = run(False)
+    l1, p1 = run(True)
+    assert torch.allclose(l0, l1, rtol=2e-3, atol=1e-7), (l0, l1)
+    for a, b in zip(p0, p1):
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)
