@@ -298,7 +298,14 @@ def run_gpu_arm(args):
                 bufs[i % 2][k].copy_(host[k], non_blocking=True)
             ready[i % 2].record(copy_stream)
 
+    host_out = [torch.empty(packed.numel()).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+
     def e2e_run(steps):
+        """every step: H2D of its inputs (copy stream, overlapping the previous step's kernels), the step, D2H of
+        its result (loss + shared-parameter gradients) into pinned memory.  The host consumes result i after it has
+        enqueued step i+1, so the device never idles on the host round trip; the last result is awaited inside the
+        timed region."""
         cur = torch.cuda.current_stream()
         for b in range(2):
             free[b].record(cur)
@@ -308,8 +315,15 @@ def run_gpu_arm(args):
             if i + 1 < steps:
                 enqueue_copy(i + 1)
             cur.wait_event(ready[i % 2])
-            out = step(bufs[i % 2], True)       # packed.cpu(): loss + shared gradients, device -> host every step
+            res = step(bufs[i % 2], False)
+            host_out[i % 2].copy_(res, non_blocking=True)   # device -> host every step
+            done[i % 2].record(cur)
             free[i % 2].record(cur)
+            if i > 0:
+                done[(i - 1) % 2].synchronize()
+                out = float(host_out[(i - 1) % 2][-1])      # the host reads step i-1's loss
+        done[(steps - 1) % 2].synchronize()
+        out = float(host_out[(steps - 1) % 2][-1])
         return out
 
     e2e_run(2)
