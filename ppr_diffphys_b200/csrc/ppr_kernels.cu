@@ -53,6 +53,8 @@ struct DevModel {
     const int4* jinfo;        // [nb] type, parent, q_start, qd_start
     const int4* jinfo2;       // [nb] ndof, depth, contact begin, contact end
     const unsigned long long* child;  // [nb] 8 x uint8 child body index (0xff = none)
+    const int* order;                 // [nb] block layout: position in the block -> body
+    const int* pos;                   // [nb] block layout: body -> position
     const float* xpj;         // [nb,7] joint_X_p
     const float* qoff;        // [nb,4] rot(joint_X_c)
     const float* axis;        // [nb,3]
@@ -151,7 +153,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // Collectives over the articulation tree, executed by EVERY thread of the group (warp or block):
 //   parent_*  : each thread obtains values held by the thread of its parent body
 //   gather_*  : each thread sums a message held by the threads of its child bodies
-// `child` packs up to 8 children as byte OFFSETS from the own slot (children follow their parent; 0 = none);
+// `child` packs up to 8 children as bytes: slot of the child + 1 (0 = none);
 // `ps` = slot of the parent (own slot if none).
 template <int NT> struct WarpComm {
     static constexpr int kThreads = NT;
@@ -182,7 +184,7 @@ template <int NT> struct WarpComm {
 #pragma unroll 1
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
-            WrenchF o = shf_wrench(mine, (int)(threadIdx.x & 31) + (int)c);
+            WrenchF o = shf_wrench(mine, c ? (int)c - 1 : (int)(threadIdx.x & 31));
             if (c) { acc.t += o.t; acc.f += o.f; }
         }
     }
@@ -190,7 +192,7 @@ template <int NT> struct WarpComm {
 #pragma unroll 1
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
-            BodyF o = shf_body(mine, (int)(threadIdx.x & 31) + (int)c);
+            BodyF o = shf_body(mine, c ? (int)c - 1 : (int)(threadIdx.x & 31));
             if (c) body_acc(acc, o);
         }
     }
@@ -319,7 +321,7 @@ template <int NT> struct BlockComm {
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
             if (c) {
-                const WrenchF w = get_wrench(msg, (int)(threadIdx.x + c));
+                const WrenchF w = get_wrench(msg, (int)c - 1);
                 acc.t += w.t; acc.f += w.f;
             }
         }
@@ -330,7 +332,7 @@ template <int NT> struct BlockComm {
 #pragma unroll 1
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
-            if (c) body_acc(acc, get_body(msg, (int)(threadIdx.x + c), tail));
+            if (c) body_acc(acc, get_body(msg, (int)c - 1, tail));
         }
     }
     // plain-barrier variant for the FK adjoint (outside the substep loop)
@@ -342,7 +344,7 @@ template <int NT> struct BlockComm {
 #pragma unroll 1
         for (int sl = 0; sl < maxc; ++sl) {
             unsigned c = (unsigned)((child >> (8 * sl)) & 0xffu);
-            if (c) body_acc(acc, get_body(msg, (int)(threadIdx.x + c), tail));
+            if (c) body_acc(acc, get_body(msg, (int)c - 1, tail));
         }
         __syncthreads();
     }
@@ -363,7 +365,7 @@ struct LaneInfo {
     int env, body, parent_slot, type, ndof, depth, qs, qds, c0, c1;
     int maxc_w;  // largest child count among the lanes of this WARP (trip count of the child-gather loops)
     bool valid, has_parent;
-    unsigned long long child;  // children as byte offsets from the own slot (child body index - own body index), 0 none
+    unsigned long long child;  // up to 8 children as bytes: slot of the child + 1, 0 = none
     JointStatic<float> js;
     F3 com;
     float aabb[7];
@@ -379,22 +381,25 @@ __device__ __forceinline__ LaneInfo lane_setup(const DevModel& M, int64_t group,
     LaneInfo L;
     const int lane = slot;
     int e_in_w, body;
-    if (body_major) { body = slot / epg; e_in_w = slot - body * epg; }
-    else { e_in_w = slot / M.nb; body = slot - e_in_w * M.nb; }
+    if (body_major) {
+        int p = slot / epg;
+        e_in_w = slot - p * epg;
+        body = p < M.nb ? M.order[p] : M.nb;   // the order balances the contact-heavy bodies over the block's warps
+    } else { e_in_w = slot / M.nb; body = slot - e_in_w * M.nb; }
     int64_t env = group * epg + e_in_w;
     L.valid = (e_in_w < epg) && (body < M.nb) && (env < n_env);
     if (!L.valid) { e_in_w = 0; body = 0; env = group * epg; }
-    const int sstride = body_major ? epg : 1;               // slot distance of consecutive bodies of one environment
-    const int seg = body_major ? e_in_w : e_in_w * M.nb;    // slot of body 0 of this environment
     L.env = (int)env; L.body = body;
     int4 ji = M.jinfo[body], j2 = M.jinfo2[body];
-    L.type = ji.x; L.has_parent = ji.y >= 0; L.parent_slot = L.has_parent ? seg + ji.y * sstride : lane;
+    // slot of body b of this lane's environment
+    auto slot_of = [&](int b) { return body_major ? M.pos[b] * epg + e_in_w : e_in_w * M.nb + b; };
+    L.type = ji.x; L.has_parent = ji.y >= 0; L.parent_slot = L.has_parent ? slot_of(ji.y) : lane;
     L.qs = ji.z; L.qds = ji.w; L.ndof = j2.x; L.depth = j2.y; L.c0 = j2.z; L.c1 = j2.w;
     unsigned long long ch = M.child[body], out = 0;
 #pragma unroll
     for (int s = 0; s < PPR_MAX_CHILD; ++s) {
         unsigned c = (unsigned)((ch >> (8 * s)) & 0xffu);
-        unsigned long long v = (c == 0xffu || !L.valid) ? 0ull : (unsigned long long)((c - (unsigned)body) * sstride);
+        unsigned long long v = (c == 0xffu || !L.valid) ? 0ull : (unsigned long long)(slot_of((int)c) + 1);
         out |= v << (8 * s);
     }
     L.child = out;
@@ -1260,6 +1265,9 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
     };
     size_t o_jinfo = add(jinfo.data(), nb * sizeof(int4)), o_jinfo2 = add(jinfo2.data(), nb * sizeof(int4));
     size_t o_child = add(child.data(), nb * sizeof(unsigned long long));
+    std::vector<int> ident(nb);
+    for (int i = 0; i < nb; ++i) ident[i] = i;
+    size_t o_order = add(ident.data(), nb * sizeof(int)), o_pos = add(ident.data(), nb * sizeof(int));
     size_t o_xpj = add(D->joint_X_p, nb * 7 * sizeof(float)), o_qoff = add(qoff.data(), nb * 4 * sizeof(float));
     size_t o_axis = add(D->joint_axis, nb * 3 * sizeof(float)), o_com = add(D->body_com, nb * 3 * sizeof(float));
     size_t o_lim = add(lim.data(), lim.size() * sizeof(float4));
@@ -1283,6 +1291,7 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
     d.epw = 32 / nb; d.maxc = maxc; d.maxdepth = maxdepth; d.big_threshold = 16;
     d.jinfo = (const int4*)(base + o_jinfo); d.jinfo2 = (const int4*)(base + o_jinfo2);
     d.child = (const unsigned long long*)(base + o_child);
+    d.order = (const int*)(base + o_order); d.pos = (const int*)(base + o_pos);
     d.xpj = (const float*)(base + o_xpj); d.qoff = (const float*)(base + o_qoff);
     d.axis = (const float*)(base + o_axis); d.com = (const float*)(base + o_com);
     d.lim = (const float4*)(base + o_lim); d.cpt = (const float4*)(base + o_cpt); d.cmat = (const int*)(base + o_cmat);
@@ -1318,6 +1327,46 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
         }
         const char* ov = getenv("PPR_COMM");
         if (ov && ov[0] >= '0' && ov[0] <= '2') m->comm = ov[0] - '0';
+    }
+    // Block layout: order of the bodies inside the block (slot = position * envs_per_block + env).  The contact pass is
+    // warp-cooperative and serial over a warp's "big" bodies (collision meshes), and the block's warps meet at two
+    // barriers per substep, so the big bodies that usually touch the ground -- the leaves of the tree: feet, hands,
+    // head (inner links count 1/32) -- are spread evenly over the warps: minimise the largest per-warp sum of their
+    // vertices (then the sum of squares) by pairwise swaps from the identity order; deterministic.
+    if (m->comm != 0) {
+        const int nt = kCommThreads[m->comm], epb = nt / nb, nw = nt / 32;
+        std::vector<int> w(nb), order(ident), pos(nb);
+        bool any_big = false;
+        for (int b = 0; b < nb; ++b) {
+            int n = jinfo2[b].w - jinfo2[b].z;
+            w[b] = n > d.big_threshold ? (nchild[b] == 0 ? 32 * n : n) : 0;
+            any_big |= w[b] > 0;
+        }
+        auto cost = [&](const std::vector<int>& o) {
+            std::vector<long long> load(nw, 0);
+            for (int p2 = 0; p2 < nb; ++p2)
+                for (int e2 = 0; e2 < epb; ++e2) load[(p2 * epb + e2) / 32] += w[o[p2]];
+            long long mx = 0, sq = 0;
+            for (long long l : load) { mx = l > mx ? l : mx; sq += l * l; }
+            return std::make_pair(mx, sq);
+        };
+        if (any_big && !getenv("PPR_NO_BALANCE")) {
+            auto best = cost(order);
+            for (bool improved = true; improved;) {
+                improved = false;
+                for (int i = 0; i < nb; ++i)
+                    for (int j = i + 1; j < nb; ++j) {
+                        std::swap(order[i], order[j]);
+                        auto c = cost(order);
+                        if (c < best) { best = c; improved = true; }
+                        else std::swap(order[i], order[j]);
+                    }
+            }
+        }
+        for (int p2 = 0; p2 < nb; ++p2) pos[order[p2]] = p2;
+        e = cudaMemcpy(base + o_order, order.data(), nb * sizeof(int), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(base + o_pos, pos.data(), nb * sizeof(int), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(m->blob); delete m; return (int)e; }
     }
     m->ckpt_every = 1;
     m->latency_envs = 1024;   // ~148 SMs x 4 schedulers x 2 warps: measured break-even of the two layouts on B200
