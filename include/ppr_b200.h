@@ -63,6 +63,11 @@ int ppr_model_create(const ppr_model_desc* desc, ppr_model_t* out);
 int ppr_model_destroy(ppr_model_t m);
 /* lab4d overwrites env.joint_X_p from torch every step (diffphys/dp_interface.py:465): HOST pointer, [nb,7]. */
 int ppr_model_set_joint_X_p(ppr_model_t m, const float* joint_X_p, void* stream);
+/* Per-environment joint_X_p, the form lab4d actually assigns (dp_interface.py:454-465: one [nb,7] block per env,
+ * because every video instance has its own bone lengths): DEVICE pointer to [n_env, nb, 7], read zero-copy by every
+ * later FK / rollout call (like wp.from_torch) -- the caller keeps it alive; articulation i of a call uses block
+ * i % n_env (FK frames are laid out [T, bs]).  NULL / 0 returns to the shared table above. */
+int ppr_model_set_joint_X_p_env(ppr_model_t m, const float* dev_joint_X_p, int64_t n_env);
 int ppr_model_set_attach(ppr_model_t m, float attach_ke, float attach_kd);
 int ppr_model_set_gravity(ppr_model_t m, const float g[3]);
 /* Checkpoint policy of the rollout (default 1): the forward pass keeps the per-substep state every `every` substeps;

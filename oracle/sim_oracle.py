@@ -157,7 +157,7 @@ def eval_fk(m: OracleModel, joint_q, joint_qd):
         p = m.joint_parent[i]
         X_wp = body_q[p] if p >= 0 else ident
         v_wp = body_qd[p] if p >= 0 else torch.zeros(bs, 6, dtype=joint_q.dtype, device=joint_q.device)
-        X_pj = m.joint_X_p[i].expand(bs, 7)
+        X_pj = m.joint_X_p[:, i] if m.joint_X_p.dim() == 3 else m.joint_X_p[i].expand(bs, 7)   # per-env [bs,nb,7] or shared
         qs, qds, jt = m.joint_q_start[i], m.joint_qd_start[i], m.joint_type[i]
         if jt == JOINT_FREE:
             X_jc = joint_q[:, qs:qs + 7]
@@ -252,7 +252,7 @@ def eval_body_joints(m: OracleModel, body_q, body_qd, joint_target, joint_act, t
     dt_, dev = body_q.dtype, body_q.device
     hp = m.has_parent[None, :, None].to(dt_)
     Xp_body = body_q[:, m.parent_idx]                                  # [bs,nb,7]
-    X_pj = m.joint_X_p[None].expand(bs, nb, 7)
+    X_pj = m.joint_X_p if m.joint_X_p.dim() == 3 else m.joint_X_p[None].expand(bs, nb, 7)
     X_wp = torch.where(m.has_parent[None, :, None], transform_mul(Xp_body, X_pj), X_pj)
     r_p = (X_wp[..., :3] - transform_point(Xp_body, m.body_com[m.parent_idx][None])) * hp
     tw_p = body_qd[:, m.parent_idx] * hp

@@ -53,6 +53,8 @@ struct DevModel {
     const int4* jinfo;        // [nb] type, parent, q_start, qd_start
     const int4* jinfo2;       // [nb] ndof, depth, contact begin, contact end
     const unsigned long long* child;  // [nb] 8 x uint8 child body index (0xff = none)
+    const float* xpj_env;             // optional DEVICE array [xpj_nenv, nb, 7]: per-environment joint_X_p (else xpj)
+    int64_t xpj_nenv;
     const int* order;                 // [nb] block layout: position in the block -> body
     const int* pos;                   // [nb] block layout: body -> position
     const float* xpj;         // [nb,7] joint_X_p
@@ -407,7 +409,7 @@ __device__ __forceinline__ LaneInfo lane_setup(const DevModel& M, int64_t group,
 #pragma unroll
     for (int s = 0; s < PPR_MAX_CHILD; ++s) if ((out >> (8 * s)) & 0xffull) nchild = s + 1;
     L.maxc_w = __reduce_max_sync(FULL, nchild);
-    const float* xp = M.xpj + 7 * body;
+    const float* xp = M.xpj_env ? M.xpj_env + ((env % M.xpj_nenv) * M.nb + body) * 7 : M.xpj + 7 * body;
     L.js.type = L.type;
     L.js.xpj = v3<float>(xp[0], xp[1], xp[2]);
     L.js.qpj = q4<float>(xp[3], xp[4], xp[5], xp[6]);
@@ -421,9 +423,6 @@ __device__ __forceinline__ LaneInfo lane_setup(const DevModel& M, int64_t group,
 
 __device__ __forceinline__ void stage_static(volatile float* st, const LaneInfo& L, F3 com_par) {
     int b = L.body;
-    st[(ST_XPJ + 0) * 32 + b] = L.js.xpj.x; st[(ST_XPJ + 1) * 32 + b] = L.js.xpj.y; st[(ST_XPJ + 2) * 32 + b] = L.js.xpj.z;
-    st[(ST_QPJ + 0) * 32 + b] = L.js.qpj.x; st[(ST_QPJ + 1) * 32 + b] = L.js.qpj.y;
-    st[(ST_QPJ + 2) * 32 + b] = L.js.qpj.z; st[(ST_QPJ + 3) * 32 + b] = L.js.qpj.w;
     st[(ST_AXIS + 0) * 32 + b] = L.js.axis.x; st[(ST_AXIS + 1) * 32 + b] = L.js.axis.y; st[(ST_AXIS + 2) * 32 + b] = L.js.axis.z;
     st[(ST_COM + 0) * 32 + b] = L.com.x; st[(ST_COM + 1) * 32 + b] = L.com.y; st[(ST_COM + 2) * 32 + b] = L.com.z;
     st[(ST_CPAR + 0) * 32 + b] = com_par.x; st[(ST_CPAR + 1) * 32 + b] = com_par.y; st[(ST_CPAR + 2) * 32 + b] = com_par.z;
@@ -432,22 +431,6 @@ __device__ __forceinline__ void stage_static(volatile float* st, const LaneInfo&
     st[(ST_QOFF + 0) * 32 + b] = L.js.qoff.x; st[(ST_QOFF + 1) * 32 + b] = L.js.qoff.y;
     st[(ST_QOFF + 2) * 32 + b] = L.js.qoff.z; st[(ST_QOFF + 3) * 32 + b] = L.js.qoff.w;
 }
-__device__ __forceinline__ F3 st_vec3(const volatile float* st, int row, int b) {
-    return v3<float>(st[row * 32 + b], st[(row + 1) * 32 + b], st[(row + 2) * 32 + b]);
-}
-template <bool QOFF>
-__device__ __forceinline__ JointStatic<float> st_joint(const volatile float* st, int b, int type) {
-    JointStatic<float> js;
-    js.type = type;
-    js.xpj = st_vec3(st, ST_XPJ, b);
-    js.qpj = q4<float>(st[(ST_QPJ + 0) * 32 + b], st[(ST_QPJ + 1) * 32 + b], st[(ST_QPJ + 2) * 32 + b],
-                       st[(ST_QPJ + 3) * 32 + b]);
-    js.axis = st_vec3(st, ST_AXIS, b);
-    js.qoff = QOFF ? q4<float>(st[(ST_QOFF + 0) * 32 + b], st[(ST_QOFF + 1) * 32 + b], st[(ST_QOFF + 2) * 32 + b],
-                               st[(ST_QOFF + 3) * 32 + b])
-                   : q4<float>(0.f, 0.f, 0.f, 1.f);
-    return js;
-}
 // per-thread parameters as five float4 quads [5][NT]: (inv_m, I0..I2) (I3..I6) (I7, I8, J0, J1) (J2..J5) (J6..J8, -);
 // `asm volatile` loads: re-issued at the point of use in every substep, never hoisted into loop-long registers
 __device__ __forceinline__ float4 lds128v(const float4* p) {
@@ -455,6 +438,24 @@ __device__ __forceinline__ float4 lds128v(const float4* p) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((unsigned)__cvta_generic_to_shared(p)));
     return v;
+}
+__device__ __forceinline__ F3 st_vec3(const volatile float* st, int row, int b) {
+    return v3<float>(st[row * 32 + b], st[(row + 1) * 32 + b], st[(row + 2) * 32 + b]);
+}
+// joint_X_p is per THREAD (two float4 quads [2][NT]: (x, y, z, qx) (qy, qz, qw, -)) because lab4d gives every
+// environment its own bone lengths (dp_interface.py:454-465); everything else of the joint is per body
+template <int NT, bool QOFF>
+__device__ __forceinline__ JointStatic<float> st_joint(const volatile float* st, const float4* xpq, int b, int type) {
+    JointStatic<float> js;
+    js.type = type;
+    const float4 a = lds128v(xpq), c = lds128v(xpq + NT);
+    js.xpj = v3<float>(a.x, a.y, a.z);
+    js.qpj = q4<float>(a.w, c.x, c.y, c.z);
+    js.axis = st_vec3(st, ST_AXIS, b);
+    js.qoff = QOFF ? q4<float>(st[(ST_QOFF + 0) * 32 + b], st[(ST_QOFF + 1) * 32 + b], st[(ST_QOFF + 2) * 32 + b],
+                               st[(ST_QOFF + 3) * 32 + b])
+                   : q4<float>(0.f, 0.f, 0.f, 1.f);
+    return js;
 }
 template <int NT>
 __device__ __forceinline__ void par_store(float4* par, float inv_m, const float* I, const float* J) {
@@ -788,7 +789,7 @@ __device__ __forceinline__ void store_wrench_row(float* base, const WrenchF& w) 
 template <int JM, bool LIMITS, bool QOFF, class Comm>
 __device__ __forceinline__ void warp_forces(Comm& comm, const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
                                             const M3F& Rb, F3 xc, const JointCtl<float>& ctl, const ContactMat<float>& cm0,
-                                            const volatile float* st, int* clist, const float* res_f_row,
+                                            const volatile float* st, const float4* xpq, int* clist, const float* res_f_row,
                                             float* grf_row, float* jaf_row, WrenchF& F, ContactRec& rec, float* ang) {
     comm.post_state(s, xc);   // published before the (long, warp-dependent) contact pass, awaited after it
     F = wrench_zero<float>();
@@ -805,7 +806,7 @@ __device__ __forceinline__ void warp_forces(Comm& comm, const DevModel& M, const
     comm.get_parent_state(s, xc, L.parent_slot, P, xcp);
     if (!L.has_parent) { P = body_identity<float>(); xcp = vzero<float>(); }
     F3 t, f, ap, ac;
-    joint_fwd<float, JM, LIMITS, QOFF>(st_joint<QOFF>(st, L.body, L.type), ctl, M.ake, M.akd, P, xcp, L.has_parent, s,
+    joint_fwd<float, JM, LIMITS, QOFF>(st_joint<Comm::kThreads, QOFF>(st, xpq, L.body, L.type), ctl, M.ake, M.akd, P, xcp, L.has_parent, s,
                                        Rb, xc, t, f, ap, ac, ang);
     WrenchF Wp = wrench_zero<float>();
     if (L.type != JT_FREE) {
@@ -831,7 +832,8 @@ template <class Comm, bool ADJ> struct SmemLayout {
     static constexpr int row = 0;
     static constexpr int st = row + (ADJ ? NW * PPR_CKPT_FLOATS * 32 : 0);
     static constexpr int par = st + PPR_NSTATIC * 32;
-    static constexpr int acc = par + PPR_NPAR * NT;
+    static constexpr int xpq = par + PPR_NPAR * NT;
+    static constexpr int acc = xpq + 8 * NT;
     static constexpr int clist = acc + (ADJ ? 20 * NT : 0);
     static constexpr int comm = clist + NW * 32 * PPR_CLIST_STRIDE;
     static constexpr int total = comm + Comm::kExFloats;
@@ -852,6 +854,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     int* clist = (int*)(smem + SL::clist) + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
     volatile float* st = smem + SL::st;
     float4* par = (float4*)(smem + SL::par) + threadIdx.x;
+    float4* xpq = (float4*)(smem + SL::xpq) + threadIdx.x;
     if (group >= A.ngroups) return;
     comm.init();
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
@@ -860,6 +863,8 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     // per-env parameters of this body / joint -> shared memory
     int64_t ebp = (int64_t)L.env * A.pstride * M.nb + L.body;
     par_store<NT>(par, A.inv_m[ebp], A.I + ebp * 9, A.inv_I + ebp * 9);
+    xpq[0] = make_float4(L.js.xpj.x, L.js.xpj.y, L.js.xpj.z, L.js.qpj.x);
+    xpq[NT] = make_float4(L.js.qpj.y, L.js.qpj.z, L.js.qpj.w, 0.f);
     JointCtl<float> ctl;
     float ke[3], kd[3];
 #pragma unroll
@@ -905,7 +910,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         WrenchF F;
         ContactRec rec;
         float ang[3];
-        warp_forces<JM, LIMITS, QOFF>(comm, M, L, lane, s, Rb, xc, ctl, cm0, st, clist, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
+        warp_forces<JM, LIMITS, QOFF>(comm, M, L, lane, s, Rb, xc, ctl, cm0, st, xpq, clist, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
                     (frame && A.out_grf) ? A.out_grf + frow * 6 : nullptr,
                     (frame && A.out_jaf) ? A.out_jaf + frow * 6 : nullptr, F, rec, ang);
         // checkpoint (coalesced: component-major rows of 32 lanes), every K-th substep
@@ -951,6 +956,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     int* clist = (int*)(smem + SL::clist) + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
     volatile float* st = smem + SL::st;
     float4* par = (float4*)(smem + SL::par) + threadIdx.x;
+    float4* xpq = (float4*)(smem + SL::xpq) + threadIdx.x;
     float4* acc = (float4*)(smem + SL::acc) + threadIdx.x;
     volatile float* roww = smem + SL::row + (threadIdx.x >> 5) * PPR_CKPT_FLOATS * 32;  // this warp's row buffer
     volatile float* row = roww + (threadIdx.x & 31);
@@ -962,6 +968,8 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     int64_t eb = (int64_t)L.env * M.nb + L.body;
     int64_t ebp = (int64_t)L.env * A.pstride * M.nb + L.body;
     par_store<NT>(par, A.inv_m[ebp], A.I + ebp * 9, A.inv_I + ebp * 9);
+    xpq[0] = make_float4(L.js.xpj.x, L.js.xpj.y, L.js.xpj.z, L.js.qpj.x);
+    xpq[NT] = make_float4(L.js.qpj.y, L.js.qpj.z, L.js.qpj.w, 0.f);
 #pragma unroll
     for (int i = 0; i < 5; ++i) acc[i * NT] = make_float4(0.f, 0.f, 0.f, 0.f);
     JointCtl<float> ctl;
@@ -1038,7 +1046,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
                 WrenchF Fr;
                 ContactRec recr;
                 float angr[3];
-                warp_forces<JM, LIMITS, QOFF>(comm, M, L, lane, sr, Rr, xcr, ctl, cm0, st, clist,
+                warp_forces<JM, LIMITS, QOFF>(comm, M, L, lane, sr, Rr, xcr, ctl, cm0, st, xpq, clist,
                                               A.res_f ? A.res_f + ((tr * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
                                               nullptr, nullptr, Fr, recr, angr);
                 float* c = scr + (tr - seg_lo) * PPR_CKPT_FLOATS * 32 + lane;
@@ -1134,7 +1142,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         BodyF adjP = body_zero<float>();
         F3 adj_xcp = vzero<float>();
         float g_target[3] = {0, 0, 0}, g_act[3] = {0, 0, 0};
-        joint_adj<float, JM, LIMITS, QOFF>(st_joint<QOFF>(st, L.body, L.type), ctl, M.ake, M.akd, P, xcp, L.has_parent, s,
+        joint_adj<float, JM, LIMITS, QOFF>(st_joint<NT, QOFF>(st, xpq, L.body, L.type), ctl, M.ake, M.akd, P, xcp, L.has_parent, s,
                                            Rb, xc, adjFp, adjF, adjP, adj_xcp, adjS, G, adj_xc, g_target, g_act, a_ke,
                                            a_kd, ang);
         adjP.x += adj_xcp;
@@ -1292,6 +1300,7 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
     d.jinfo = (const int4*)(base + o_jinfo); d.jinfo2 = (const int4*)(base + o_jinfo2);
     d.child = (const unsigned long long*)(base + o_child);
     d.order = (const int*)(base + o_order); d.pos = (const int*)(base + o_pos);
+    d.xpj_env = nullptr; d.xpj_nenv = 0;
     d.xpj = (const float*)(base + o_xpj); d.qoff = (const float*)(base + o_qoff);
     d.axis = (const float*)(base + o_axis); d.com = (const float*)(base + o_com);
     d.lim = (const float4*)(base + o_lim); d.cpt = (const float4*)(base + o_cpt); d.cmat = (const int*)(base + o_cmat);
@@ -1403,6 +1412,13 @@ extern "C" int ppr_model_set_gravity(ppr_model_t m, const float g[3]) {
     if (!check(m)) return PPR_E_HANDLE;
     if (!g) return PPR_E_ARG;
     m->d.g[0] = g[0]; m->d.g[1] = g[1]; m->d.g[2] = g[2];
+    return 0;
+}
+extern "C" int ppr_model_set_joint_X_p_env(ppr_model_t m, const float* dev_joint_X_p, int64_t n_env) {
+    if (!check(m)) return PPR_E_HANDLE;
+    if ((dev_joint_X_p != nullptr) != (n_env > 0) || n_env < 0) return PPR_E_ARG;
+    m->d.xpj_env = dev_joint_X_p;
+    m->d.xpj_nenv = n_env;
     return 0;
 }
 extern "C" int ppr_model_set_checkpoint_every(ppr_model_t m, int32_t every) {

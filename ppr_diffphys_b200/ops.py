@@ -101,10 +101,22 @@ class SimEnv:
 
     @joint_X_p.setter
     def joint_X_p(self, value):
-        v = torch.as_tensor(value).detach().float().cpu().reshape(-1, 7)[: self.nb].contiguous()
+        """``env.joint_X_p = tensor`` as lab4d does every step (dp_interface.py:465).  [nb,7]: one table shared by
+        all envs (uploaded).  [n_env*nb,7]: one block per env, the reference's own shape (every video instance has
+        its own bone lengths) -- a CUDA tensor is used in place, zero-copy like wp.from_torch, and kept alive here."""
+        v = torch.as_tensor(value).detach().reshape(-1, 7)
+        if v.shape[0] > self.nb:
+            assert v.shape[0] % self.nb == 0, "joint_X_p must have a multiple of nb rows"
+            v = v.to(self.device, torch.float32).contiguous()
+            self._joint_X_p = v
+            _lib.check(self._lib.ppr_model_set_joint_X_p_env(self._h, C.c_void_p(v.data_ptr()), v.shape[0] // self.nb),
+                       "ppr_model_set_joint_X_p_env")
+            return
+        v = v.float().cpu()[: self.nb].contiguous()
         self._joint_X_p = v
         with torch.cuda.device(self.device):
             torch.cuda.current_stream().synchronize()  # the host staging buffer is reused by the library
+            _lib.check(self._lib.ppr_model_set_joint_X_p_env(self._h, None, 0), "ppr_model_set_joint_X_p_env")
             _lib.check(self._lib.ppr_model_set_joint_X_p(self._h, C.c_void_p(v.data_ptr()), _stream()),
                        "ppr_model_set_joint_X_p")
 

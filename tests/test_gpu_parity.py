@@ -370,8 +370,8 @@ def test_checkpoint_every_k_recompute(robot, every):
 @pytest.mark.parametrize("robot", ["laikago", "human", "quad", "mixed"])
 def test_latency_layout_equals_throughput_layout(robot):
     """Small batches run one environment per warp (ppr_model_set_latency_envs), large ones the block / warp packing
-    chosen for throughput: same arithmetic per body, so trajectories and force side channels agree bit for bit and
-    gradients to rounding."""
+    chosen for throughput: same arithmetic per body, so trajectories, force side channels and gradients agree to
+    rounding."""
     from ppr_diffphys_b200 import SimEnv
     stride, F, bs = 16, 3, 11
     T = stride * (F - 1) + 1
@@ -392,9 +392,10 @@ def test_latency_layout_equals_throughput_layout(robot):
         ((pos ** 2).sum() + (vel ** 2).sum() * 0.01).backward()
         out.append((pos.detach(), vel.detach(), torch.stack(caller.grfs), torch.stack(caller.jafs),
                     [a[k].grad for k in KEYS]))
-    for x, y in zip(out[0][:4], out[1][:4]):
-        assert torch.equal(x, y)
-    # the adjoint instances of the two layouts are separate compilations (different fma contraction): last-bit level
+    # the kernel instances of the two layouts are separate compilations (different fma contraction): last-bit level
+    # (joint forces amplify a last-bit pose difference by the 8e3..1.6e4 N/m attachment stiffness)
+    for name, tol, x, y in zip(("pos", "vel", "grf", "jaf"), (2e-6, 2e-6, 1e-4, 1e-4), out[0][:4], out[1][:4]):
+        assert rel(x, y.double().cpu()) < tol, (name, rel(x, y.double().cpu()))
     for k, x, y in zip(KEYS, out[0][4], out[1][4]):
         assert rel(x, y.double().cpu()) < 1e-5, k
 
@@ -453,6 +454,66 @@ def test_joint_X_p_setter_changes_fk():
     env.joint_X_p = xp
     b1, _ = env.fk(q, qd)
     assert abs(float(b1[0, 1, 0] - b0[0, 1, 0]) - 0.1) < 1e-6
+
+
+@pytest.mark.parametrize("robot", ["laikago", "human"])
+def test_per_env_joint_X_p_parity(robot):
+    """lab4d assigns env.joint_X_p with ONE BLOCK PER ENV (dp_interface.py:454-465: per-instance bone lengths):
+    FK, trajectories and gradients against the oracle given the same [bs, nb, 7] table; then back to the shared
+    table."""
+    from oracle import sim_oracle as so
+    from ppr_diffphys_b200 import SimEnv
+    stride, F, bs = 16, 3, 6
+    T = stride * (F - 1) + 1
+    rm, d = make_inputs(robot, bs=bs, T=T, seed=5)
+    g = torch.Generator().manual_seed(9)
+    xp = torch.as_tensor(rm.joint_X_p, dtype=torch.float64)[None].repeat(bs, 1, 1)
+    xp[:, 1:, :3] *= 1.0 + 0.2 * (torch.rand(bs, 1, 1, generator=g, dtype=torch.float64) - 0.5)   # bone-length scale per env
+    dq = torch.randn(bs, rm.nb, 4, generator=g, dtype=torch.float64) * 0.03
+    q = xp[:, :, 3:] + dq
+    xp[:, 1:, 3:] = (q / q.norm(dim=-1, keepdim=True))[:, 1:]
+    xp = xp.float().double()
+    m = so.OracleModel(rm)
+    m.joint_X_p = xp
+    # settle on the ground with the per-env skeleton
+    bq, _ = so.eval_fk(m, d["q_init"], d["qd_init"])
+    cb = torch.as_tensor(rm.contact_body, dtype=torch.long)
+    pts = so.quat_rotate(bq[:, cb, 3:7], torch.as_tensor(rm.contact_point, dtype=torch.float64)[None].expand(bs, -1, 3))
+    d["q_init"][:, 1] -= (bq[:, cb, 1] + pts[..., 1]).min(1)[0] + 0.002
+    d = {k: v.float().double() for k, v in d.items()}
+    dev = torch.device("cuda:0")
+    env = SimEnv(rm)
+    env.joint_X_p = xp.reshape(-1, 7).to(dev, torch.float32)
+    # FK with T frames x bs envs: articulation i uses block i % bs
+    q2 = torch.stack([d["q_init"], d["q_init"] * 0.9]).float().to(dev)          # [2, bs, nq]
+    qd2 = torch.stack([d["qd_init"], d["qd_init"] * 0.5]).float().to(dev)
+    fbq, fbqd = env.fk(q2.reshape(2 * bs, -1), qd2.reshape(2 * bs, -1))
+    for t in range(2):
+        obq, obqd = so.eval_fk(m, q2[t].double().cpu(), qd2[t].double().cpu())
+        assert (fbq.view(2, bs, rm.nb, 7)[t].cpu().double() - obq).abs().max() < 5e-6
+        assert (fbqd.view(2, bs, rm.nb, 6)[t].cpu().double() - obqd).abs().max() < 5e-5
+    a, _, _ = flat_args(d, dev)
+    pos, vel, caller = run_cuda(env, a, bs, T, stride)
+    o = {k: d[k].clone().requires_grad_(True) for k in KEYS}
+    opos, ovel, ogrf, ojaf = so.rollout(m, o["q_init"], o["qd_init"], o["torques"], o["res_f"], o["refs"],
+                                        o["target_ke"], o["target_kd"], o["body_inv_mass"], o["body_inertia"],
+                                        o["body_inv_inertia"], 5e-4, stride, F)
+    assert ogrf.abs().max() > 1.0
+    assert (pos.cpu().double() - opos.detach().reshape(F, -1, 7)).abs().max() <= POS_TOL
+    wp = torch.randn(opos.shape, generator=g, dtype=torch.float64)
+    wv = torch.randn(ovel.shape, generator=g, dtype=torch.float64) * 0.1
+    torch.autograd.backward([pos, vel], [wp.reshape(F, -1, 7).to(dev, torch.float32),
+                                         wv.reshape(F, -1, 6).to(dev, torch.float32)])
+    grads = torch.autograd.grad((opos * wp).sum() + (ovel * wv).sum(), [o[k] for k in KEYS])
+    tol = GRAD_RTOL_STIFF if robot == "laikago" else GRAD_RTOL
+    for k, gr in zip(KEYS, grads):
+        assert rel(a[k].grad, gr) <= tol, (k, rel(a[k].grad, gr))
+    # back to one shared table: same result as a fresh model
+    env.joint_X_p = torch.as_tensor(rm.joint_X_p)
+    a2, _, _ = flat_args(d, dev, requires_grad=False)
+    p_shared, _, _ = run_cuda(env, a2, bs, T, stride)
+    p_fresh, _, _ = run_cuda(SimEnv(rm), a2, bs, T, stride)
+    assert torch.equal(p_shared, p_fresh) and not torch.equal(p_shared, pos.detach())
 
 
 def test_forward_kinematics_reference_quirks():
