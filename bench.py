@@ -375,6 +375,19 @@ def run_gpu_arm(args):
                                "e2e": d["e2e"]["value"]})
             except Exception as ex:
                 others.append({"workload": wname, "error": repr(ex)})
+        # BASELINE.json configs[0] (the reference's own recipe: laikago, mi-pace clip, 10 windows x 24 frames = 760
+        # substeps, 3 MLPs + FK + rollout + se3 losses + backward + AdamW): seconds per optimisation iteration through
+        # the caller loop of ppr_diffphys_b200.imitation, one CUDA-graph replay per iteration
+        try:
+            ex_py = os.path.join(ROOT, "examples", "run_imitation.py")
+            out = subprocess.run([sys.executable, ex_py, "--seqname", "mi-pace", "--iters", "41", "--log-every", "1000"],
+                                 capture_output=True, text=True, timeout=300).stdout.strip().splitlines()[-1]
+            d = json.loads(out)
+            others.append({"workload": "imitation-mi-pace-10x760", "ms_per_iteration": d["median_iter_ms"],
+                           "value": d["env_steps_per_sec"], "unit": "env-steps/s", "cuda_graph": d["cuda_graph"],
+                           "loss_traj_first": d["loss_traj_first"], "loss_traj_last": d["loss_traj_last"]})
+        except Exception as ex:
+            others.append({"workload": "imitation-mi-pace-10x760", "error": repr(ex)})
     line = {
         "metric": "env_steps_per_sec_fwd_bwd", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,

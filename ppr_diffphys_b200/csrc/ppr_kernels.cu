@@ -83,7 +83,10 @@ struct ppr_model {
     int comm;                 // env packing of the rollout kernels: 0 per warp (128-thread blocks), 1 per 96-thread
                               // block, 2 per 160-thread block
 };
-static const int kCommThreads[3] = {128, 96, 160};
+#ifndef PPR_NT1
+#define PPR_NT1 96
+#endif
+static const int kCommThreads[3] = {128, PPR_NT1, 160};
 #define PPR_MAGIC 0x50505231u
 
 // ----------------------------------------------------------------------------------------------- lane helpers
@@ -1496,10 +1499,10 @@ template <class K> static cudaError_t launch_rollout(K kernel, size_t smem, unsi
             else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, d_, A); \
             else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, d_, A); \
         } else if (comm_ == 1) {                                                                                     \
-            typedef BlockComm<96> C_;                                                                                \
-            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, d_, A); \
-            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, d_, A); \
-            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 96, st, d_, A); \
+            typedef BlockComm<PPR_NT1> C_;                                                                             \
+            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, PPR_NT1, st, d_, A); \
+            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, PPR_NT1, st, d_, A); \
+            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, PPR_NT1, st, d_, A); \
         } else {                                                                                                     \
             typedef BlockComm<160> C_;                                                                               \
             if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, d_, A); \
