@@ -1,10 +1,12 @@
 // sm_100a kernels + C ABI of the rollout hot path (see include/ppr_b200.h for the boundary and the reference
 // call sites each entry point replaces).
 //
-// Mapping: one THREAD per rigid body. Environments are packed either per WARP (floor(32/nb) envs per warp, tree
-// exchange by warp shuffles) or per BLOCK (floor(NT/nb) envs per block of NT threads, tree exchange through shared
-// memory + split-phase mbarriers) -- whichever wastes fewer lanes: human has 19 bodies, i.e. 59 % lane use per warp
-// but 99 % with 5 envs in a 96-thread block. The two are the `Comm` policy of the kernels below.
+// Mapping: one THREAD per rigid body. Environments are packed either per WARP (floor(32/nb) envs per warp, slot =
+// env * nb + body, tree exchange by warp shuffles) or per BLOCK (floor(NT/nb) envs per block of NT threads, body-major
+// slots = position * envs + env, tree exchange through float4 areas of shared memory with one split-phase mbarrier and
+// one hardware barrier per substep) -- whichever wastes fewer lanes: human has 19 bodies, i.e. 59 % lane use per warp
+// but 99 % with 5 envs in a 96-thread block. The two are the `Comm` policy of the kernels below; batches too small
+// to fill the GPU run one env per warp (latency layout, rollout_geometry).
 // The body state (13 floats) lives in registers for the whole rollout; parent/child exchange of states and
 // wrenches follows the static articulation tree with ordered reads (no atomics -> deterministic, unlike the
 // reference's atomic_add/sub at integrator_euler.py:179,449,451).  The time loop is inside the kernel: one launch
