@@ -349,6 +349,19 @@ def run_gpu_arm(args):
                 "rollout_backward_kernel"]
     except Exception:
         pass
+    # secondary (honest) compute bound, SURVEY.md 8(d): executed FP32 flops per env-step (2 FFMA + FADD + FMUL thread
+    # instructions, from the committed ncu capture) x measured kernel rate, against 148 SMs x 128 lanes x 2 x SM clock
+    fp32 = None
+    try:
+        fl = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]["fp32_flops_per_env_step"]
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        peak_tf = 148 * 128 * 2 * mhz * 1e6 / 1e12
+        f_tf = fl["rollout_forward_kernel"] * bs * window / (fwd_ms * 1e-3) / 1e12
+        b_tf = fl["rollout_backward_kernel"] * bs * window / (bwd_ms * 1e-3) / 1e12
+        fp32 = {"flops_per_env_step": fl, "peak_tflops": peak_tf, "forward_tflops": f_tf, "backward_tflops": b_tf,
+                "forward_frac": f_tf / peak_tf, "backward_frac": b_tf / peak_tf}
+    except Exception:
+        pass
     bwd_gbs = ab["bwd"] * bs * window / (bwd_ms * 1e-3) / 1e9
     fwd_gbs = ab["fwd"] * bs * window / (fwd_ms * 1e-3) / 1e9
     value = env_steps / (ms / args.steps * 1e-3)
@@ -407,6 +420,7 @@ def run_gpu_arm(args):
                      "algorithmic_bytes_per_env_step": ab,
                      "forward_kernel": {"achieved": fwd_gbs, "frac": fwd_gbs / peak_gbs},
                      "fwd_bwd_combined_frac": ab["fwdbwd"] * bs * window / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak_gbs,
+                     "fp32": fp32,
                      "note": "the path is FP32-issue / latency bound, not HBM bound (SURVEY.md 8d)"},
         "e2e": {"value": env_steps / (ms_e2e / args.steps * 1e-3), "unit": "env-steps/s",
                 "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 4 * (2 * nqd + nb + 1),
