@@ -149,6 +149,16 @@ int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t fram
                          float* adj_body_inv_inertia, /* [bs*nb,3,3] */
                          const void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- se3 pose / twist loss (replaces se3_loss, dp_utils.py:113-138 with rot_angle,
+ * geom_utils.py:37-46, called at dp_model.py:777,794,800) ------------------------------------------------------
+ * n pairs of dim = 7 (xyz + quaternion xyzw) or dim = 6 (xyz + axis-angle) rows:
+ *   loss[i] = |p.xyz - g.xyz|^2 + rot_ratio * acos(clamp((tr(R_p R_g^T) - 1)/2, -1 + 1e-4, 1 - 1e-4)),  0 if a row has NaN.
+ * backward: adj_pred [n,dim] (and adj_gt [n,dim] unless NULL) are OVERWRITTEN with adj_loss[i] * dloss[i]/d(.). */
+int ppr_se3_loss_forward(int64_t n, int32_t dim, const float* pred, const float* gt, float rot_ratio, float* loss,
+                         void* stream);
+int ppr_se3_loss_backward(int64_t n, int32_t dim, const float* pred, const float* gt, float rot_ratio,
+                          const float* adj_loss, float* adj_pred, float* adj_gt, void* stream);
+
 /* Number of kernels the library has launched since load (bench.py's gpu_launches). */
 int64_t ppr_launch_count(void);
 

@@ -19,6 +19,7 @@
 
 #include "../../include/ppr_b200.h"
 #include "../../ppr_diffphys_b200/csrc/ppr_body.h"
+#include "../../ppr_diffphys_b200/csrc/ppr_loss.h"
 
 using namespace ppr;
 
@@ -347,6 +348,22 @@ int fk_backward(const ppr_model_desc* d, int64_t n, const T* jq, const T* jqd, c
 
 PPR_CPU_API(f32, float)
 PPR_CPU_API(f64, double)
+
+// se3 loss + adjoint in float64 through the SAME scalar-templated functions the CUDA kernels instantiate in float32
+// (ppr_loss.h): lets the CPU suite check the hand-written adjoint against torch autograd without a GPU.
+#define PPR_CPU_SE3(SUF, T)                                                                                          \
+    extern "C" int ppr_cpu_se3_loss_##SUF(int64_t n, int dim, const T* pred, const T* gt, T ratio, T* loss,          \
+                                          const T* adj_loss, T* adj_pred, T* adj_gt) {                               \
+        for (int64_t i = 0; i < n; ++i) {                                                                            \
+            loss[i] = ppr::se3_pair_loss<T>(dim, pred + i * dim, gt + i * dim, ratio, T(1e-4));                      \
+            if (adj_loss)                                                                                            \
+                ppr::se3_pair_loss_adj<T>(dim, pred + i * dim, gt + i * dim, ratio, T(1e-4), adj_loss[i],            \
+                                          adj_pred + i * dim, adj_gt ? adj_gt + i * dim : nullptr);                  \
+        }                                                                                                            \
+        return 0;                                                                                                    \
+    }
+PPR_CPU_SE3(f64, double)
+PPR_CPU_SE3(f32, float)
 
 extern "C" int ppr_cpu_num_threads(void) {
 #ifdef _OPENMP

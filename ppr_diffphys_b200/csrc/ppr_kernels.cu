@@ -27,6 +27,7 @@
 
 #include "../../include/ppr_b200.h"
 #include "ppr_body.h"
+#include "ppr_loss.h"
 
 using namespace ppr;
 typedef V3<float> F3;
@@ -1605,4 +1606,50 @@ extern "C" int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, i
     cudaStream_t st = (cudaStream_t)stream;
     if (m->ckpt_every > 1) PPR_LAUNCH_ROLLOUT(rollout_backward_kernel, true, , true);
     PPR_LAUNCH_ROLLOUT(rollout_backward_kernel, true, , false);
+}
+
+// ----------------------------------------------------------------------------------------------- se3 loss
+// One thread per (pred, gt) pair; see ppr_loss.h.  Replaces the ~330-400 torch kernels of one se3_loss call
+// (forward + backward) by two launches.
+__global__ void __launch_bounds__(256)
+se3_loss_forward_kernel(int64_t n, int dim, const float* __restrict__ pred, const float* __restrict__ gt, float ratio,
+                        float eps, float* __restrict__ loss) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float p[7], g[7];
+    for (int k = 0; k < dim; ++k) { p[k] = pred[i * dim + k]; g[k] = gt[i * dim + k]; }
+    loss[i] = se3_pair_loss<float>(dim, p, g, ratio, eps);
+}
+__global__ void __launch_bounds__(256)
+se3_loss_backward_kernel(int64_t n, int dim, const float* __restrict__ pred, const float* __restrict__ gt, float ratio,
+                         float eps, const float* __restrict__ adj_loss, float* __restrict__ adj_pred,
+                         float* __restrict__ adj_gt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float p[7], g[7], ap[7], ag[7];
+    for (int k = 0; k < dim; ++k) { p[k] = pred[i * dim + k]; g[k] = gt[i * dim + k]; }
+    se3_pair_loss_adj<float>(dim, p, g, ratio, eps, adj_loss[i], ap, adj_gt ? ag : nullptr);
+    for (int k = 0; k < dim; ++k) {
+        adj_pred[i * dim + k] = nan0(ap[k]);
+        if (adj_gt) adj_gt[i * dim + k] = nan0(ag[k]);
+    }
+}
+
+extern "C" int ppr_se3_loss_forward(int64_t n, int32_t dim, const float* pred, const float* gt, float rot_ratio,
+                                    float* loss, void* stream) {
+    if (n < 0 || (dim != 6 && dim != 7) || !pred || !gt || !loss) return PPR_E_ARG;
+    if (n == 0) return 0;
+    se3_loss_forward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, dim, pred, gt, rot_ratio,
+                                                                                         1e-4f, loss);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+extern "C" int ppr_se3_loss_backward(int64_t n, int32_t dim, const float* pred, const float* gt, float rot_ratio,
+                                     const float* adj_loss, float* adj_pred, float* adj_gt, void* stream) {
+    if (n < 0 || (dim != 6 && dim != 7) || !pred || !gt || !adj_loss || !adj_pred) return PPR_E_ARG;
+    if (n == 0) return 0;
+    se3_loss_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n, dim, pred, gt, rot_ratio, 1e-4f, adj_loss, adj_pred, adj_gt);
+    g_launches++;
+    return (int)cudaGetLastError();
 }

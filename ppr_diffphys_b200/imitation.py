@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from .model import ASSET_DIR, load_robot
-from .ops import ForwardKinematics, ForwardWarp, SimEnv, convert_ppr_warp
+from .ops import ForwardKinematics, ForwardWarp, Se3Loss, SimEnv, convert_ppr_warp
 
 
 # ----------------------------------------------------------------------------------------- geometry (torch, xyzw)
@@ -56,8 +56,9 @@ def rot_angle(mat, eps=1e-4):
     return torch.acos(cos.clamp(-1 + eps, 1 - eps))
 
 
-def se3_loss(pred, gt, rot_ratio=0.1):
-    """dp_utils.py:113-138 for (...,7) poses (xyzw) or (...,6) twists."""
+def se3_loss_torch(pred, gt, rot_ratio=0.1):
+    """dp_utils.py:113-138 for (...,7) poses (xyzw) or (...,6) twists, composed from torch ops (any device / dtype):
+    the definition the fused kernel is tested against."""
     nan = torch.logical_or(pred.sum(-1).isnan(), gt.sum(-1).isnan())
     trn = (pred[..., :3] - gt[..., :3]).pow(2).sum(-1)
     if pred.shape[-1] == 7:
@@ -67,6 +68,14 @@ def se3_loss(pred, gt, rot_ratio=0.1):
                         quat_to_matrix(axis_angle_to_quat(gt[..., 3:])).transpose(-1, -2))
     loss = trn + rot * rot_ratio
     return torch.where(nan, torch.zeros_like(loss), loss)
+
+
+def se3_loss(pred, gt, rot_ratio=0.1):
+    """dp_utils.py:113-138 through the fused kernel pair (ops.Se3Loss: one launch forward, one backward).  CUDA
+    tensors only -- there is no CPU path; `se3_loss_torch` is the composed definition it is tested against."""
+    if not pred.is_cuda:
+        raise RuntimeError("se3_loss needs CUDA tensors (the composed torch definition is se3_loss_torch)")
+    return Se3Loss.apply(pred, gt.to(pred.device), rot_ratio)
 
 
 def reduce_loss(loss_seq):

@@ -341,3 +341,37 @@ class ForwardWarp(torch.autograd.Function):
                 pick(4, g["refs"], sh["refs"]), pick(5, g["target_ke"], sh["ke"]), pick(6, g["target_kd"], sh["kd"]),
                 body_mass_grad, pick(8, g["body_inv_mass"], sh["inv_m"]), pick(9, g["body_inertia"], sh["I"]),
                 pick(10, g["body_inv_inertia"], sh["inv_I"]), None)
+
+
+class Se3Loss(torch.autograd.Function):
+    """``Se3Loss.apply(pred[...,7|6], gt[...,7|6], rot_ratio) -> loss[...]`` -- the reference's ``se3_loss``
+    (dp_utils.py:113-138; poses xyz + quaternion xyzw, or twists xyz + axis-angle) as ONE kernel forward and one
+    backward instead of the ~330-400 elementwise torch kernels of the composed expression."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, rot_ratio=0.1):
+        assert pred.is_cuda and pred.shape == gt.shape and pred.shape[-1] in (6, 7)
+        dim = pred.shape[-1]
+        p = _f32c(pred, pred.device)
+        g = _f32c(gt, pred.device)
+        n = p.numel() // dim
+        loss = torch.empty(pred.shape[:-1], device=pred.device, dtype=torch.float32)
+        with torch.cuda.device(pred.device):
+            _lib.check(_lib.lib().ppr_se3_loss_forward(n, dim, _ptr(p), _ptr(g), C.c_float(rot_ratio), _ptr(loss),
+                                                       _stream()), "ppr_se3_loss_forward")
+        ctx.save_for_backward(p, g)
+        ctx.rot_ratio, ctx.dim = float(rot_ratio), dim
+        return loss
+
+    @staticmethod
+    def backward(ctx, adj_loss):
+        p, g = ctx.saved_tensors
+        dim = ctx.dim
+        n = p.numel() // dim
+        a = _f32c(adj_loss, p.device)
+        ap = torch.empty_like(p)
+        ag = torch.empty_like(g) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(p.device):
+            _lib.check(_lib.lib().ppr_se3_loss_backward(n, dim, _ptr(p), _ptr(g), C.c_float(ctx.rot_ratio), _ptr(a),
+                                                        _ptr(ap), _ptr(ag), _stream()), "ppr_se3_loss_backward")
+        return (ap if ctx.needs_input_grad[0] else None), ag, None

@@ -79,3 +79,56 @@ def test_graphed_step_matches_eager_iterations():
     assert torch.allclose(l0, l1, rtol=2e-3, atol=1e-7), (l0, l1)
     for a, b in zip(p0, p1):
         assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("noise", [0.3, 0.03])
+@pytest.mark.parametrize("dim", [7, 6])
+def test_fused_se3_loss_matches_composed_torch_definition(dim, noise):
+    """ops.Se3Loss (one kernel forward, one backward, through the C ABI) == se3_loss_torch + autograd on the same
+    float32 CUDA tensors (the reference's definition, dp_utils.py:113-138), at the imitation loop's shapes; the float64
+    ground truth decides which of the two float32 evaluations may be further off."""
+    from ppr_diffphys_b200 import _lib
+    from ppr_diffphys_b200.imitation import se3_loss, se3_loss_torch
+    g = torch.Generator().manual_seed(3)
+    shape = (10, 24, 13, dim)
+    pred = torch.randn(shape, generator=g)
+    gt = pred + noise * torch.randn(shape, generator=g)   # 0.03: the small-angle regime the training loop lives in
+    if dim == 7:
+        gt[..., 3:] = gt[..., 3:] / gt[..., 3:].norm(dim=-1, keepdim=True)     # sim poses are unit, queries are not
+    pred[0, 0, 0] = gt[0, 0, 0]
+    pred[0, 0, 1, 2] = float("nan")
+    w = torch.rand(shape[:-1], generator=g).cuda()
+    out = []
+    for fn in (se3_loss_torch, se3_loss):
+        p = pred.clone().cuda().requires_grad_(True)
+        q = gt.clone().cuda().requires_grad_(True)
+        n0 = _lib.launch_count()
+        l = fn(p, q)
+        (l * w).sum().backward()
+        out.append((l.detach(), p.grad, q.grad, _lib.launch_count() - n0))
+    assert out[1][3] == 2 and out[0][3] == 0                       # exactly two launches of this library
+    ok = torch.ones(shape[:-1], dtype=torch.bool, device="cuda")
+    ok[0, 0, 1] = False                                            # NaN row: 0 / zero gradient (torch: NaN gradient)
+    assert torch.allclose(out[0][0], out[1][0], rtol=1e-4, atol=2e-5)
+    assert float(out[1][0][0, 0, 1]) == 0.0 and not out[1][1][0, 0, 1].any()
+    p64 = pred.clone().double().cuda().requires_grad_(True)
+    q64 = gt.clone().double().cuda().requires_grad_(True)
+    (se3_loss_torch(p64, q64) * w.double()).sum().backward()
+    # rot_angle's clamp (geom_utils.py:43) makes the gradient DISCONTINUOUS at cos = 1 - 1e-4: two float32 evaluations
+    # may land on different sides for a pair within rounding of it -- such pairs are not comparable
+    from ppr_diffphys_b200.imitation import axis_angle_to_quat, quat_to_matrix
+    with torch.no_grad():
+        rp, rg = p64[..., 3:], q64[..., 3:]
+        if dim == 6:
+            rp, rg = axis_angle_to_quat(rp), axis_angle_to_quat(rg)
+        cos = ((quat_to_matrix(rp) * quat_to_matrix(rg)).sum((-1, -2)) - 1) / 2
+        ok &= ~((cos - (1 - 1e-4)).abs() < 5e-6) & ~((cos + (1 - 1e-4)).abs() < 5e-6)
+    assert float(ok.float().mean()) > 0.95
+    for a, b, t in ((out[0][1], out[1][1], p64.grad), (out[0][2], out[1][2], q64.grad)):
+        assert torch.isfinite(b).all()
+        scale = t[ok].abs().max()
+        err_fused = float((b.double() - t)[ok].abs().max() / scale)
+        err_torch = float((a.double() - t)[ok].abs().max() / scale)
+        assert err_fused < max(2e-4, 3 * err_torch), (err_fused, err_torch)
+    with pytest.raises(RuntimeError):
+        se3_loss(pred, gt)                                         # CPU tensors: no CPU path

@@ -53,15 +53,15 @@ def test_se3_loss_poses_and_twists():
     ident = torch.tensor([0.0, 0, 0, 0, 0, 0, 1.0], dtype=torch.float64)
     ang = 0.3
     other = torch.tensor([1.0, 2.0, -1.0, 0, math.sin(ang / 2), 0, math.cos(ang / 2)], dtype=torch.float64)
-    l = im.se3_loss(other[None], ident[None])
+    l = im.se3_loss_torch(other[None], ident[None])
     assert abs(float(l) - (6.0 + 0.1 * ang)) < 1e-9
-    assert float(im.se3_loss(ident[None], ident[None])) <= 0.1 * math.acos(1 - 1e-4) + 1e-12   # rot_angle's eps clamp
+    assert float(im.se3_loss_torch(ident[None], ident[None])) <= 0.1 * math.acos(1 - 1e-4) + 1e-12   # rot_angle's eps clamp
     tw_a = torch.tensor([0.0, 0, 0, 0.2, 0, 0], dtype=torch.float64)
     tw_b = torch.tensor([0.5, 0, 0, 0.0, 0, 0], dtype=torch.float64)
-    assert abs(float(im.se3_loss(tw_a[None], tw_b[None])) - (0.25 + 0.1 * 0.2)) < 1e-9
+    assert abs(float(im.se3_loss_torch(tw_a[None], tw_b[None])) - (0.25 + 0.1 * 0.2)) < 1e-9
     bad = other.clone()
     bad[0] = float("nan")
-    assert float(im.se3_loss(bad[None], ident[None])) == 0.0
+    assert float(im.se3_loss_torch(bad[None], ident[None])) == 0.0
 
 
 def test_rotate_frame_and_compose_delta():
@@ -88,3 +88,86 @@ def test_motion_clip_assets_and_parse():
     m = im.parse_amp(torch.as_tensor(frames))
     assert m["pos"].shape[-1] == 3 and m["orn"].shape[-1] == 4 and m["jang"].shape[-1] == 12
     assert np.allclose(np.linalg.norm(m["orn"].numpy(), axis=-1), 1.0, atol=1e-4)
+
+
+def test_se3_loss_adjoint_f64_equals_autograd():
+    """ppr_loss.h (the scalar-templated loss + hand-written adjoint the CUDA kernels instantiate in float32) compiled
+    in float64 inside the CPU port == torch autograd of the composed definition, including small-angle twists, a
+    clamped (identical) pair and a NaN row."""
+    import ctypes as C
+    from oracle import cpu_port
+    lib = cpu_port.lib()
+    g = torch.Generator().manual_seed(0)
+    for dim in (7, 6):
+        n = 300
+        pred = torch.randn(n, dim, generator=g, dtype=torch.float64)
+        gt = torch.randn(n, dim, generator=g, dtype=torch.float64)
+        if dim == 6:
+            pred[:5, 3:] = 0
+            gt[:5, 3:] *= 1e-9
+            pred[5:10, 3:] *= 1e-8
+        pred[20] = gt[20]
+        pred[21, 0] = float("nan")
+        pred.requires_grad_(True)
+        gt.requires_grad_(True)
+        w = torch.rand(n, generator=g, dtype=torch.float64)
+        l = im.se3_loss_torch(pred, gt)
+        (l * w).sum().backward()
+        loss, ap, ag = np.zeros(n), np.zeros((n, dim)), np.zeros((n, dim))
+        P, G, W = pred.detach().numpy().copy(), gt.detach().numpy().copy(), w.numpy().copy()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        lib.ppr_cpu_se3_loss_f64(C.c_int64(n), dim, vp(P), vp(G), C.c_double(0.1), vp(loss), vp(W), vp(ap), vp(ag))
+        ok = np.ones(n, bool)
+        ok[21] = False                      # NaN row: loss 0 and zero gradient here, NaN gradient in torch
+        if dim == 6:
+            ok[:10] = False                 # |v| -> 0: torch's norm() has no gradient at 0; checked separately
+        assert np.abs(loss - l.detach().numpy())[ok].max() < 1e-12
+        assert np.abs(ap - pred.grad.numpy())[ok].max() < 1e-11 and np.abs(ag - gt.grad.numpy())[ok].max() < 1e-11
+        assert loss[21] == 0 and not ap[21].any() and not ap[20, 3:].any()
+        assert np.isfinite(ap).all() and np.isfinite(ag).all()
+        if dim == 6:
+            assert np.abs(loss - l.detach().numpy())[:10].max() < 1e-12
+            assert np.abs(ap[5:10] - pred.grad.numpy()[5:10]).max() < 1e-9   # tiny but non-zero angles
+
+
+def test_se3_loss_float32_accuracy_beats_trace_form():
+    """The float32 instantiation of ppr_loss.h (relative-quaternion angle, what the CUDA kernel runs) against the
+    float64 truth: at least as accurate as the float32 trace / acos form of the composed definition, by 1-2 orders of
+    magnitude at the small angles of the training loop.  Pairs within rounding of rot_angle's clamp boundary are
+    excluded (the gradient is discontinuous there)."""
+    import ctypes as C
+    from oracle import cpu_port
+    lib = cpu_port.lib()
+    g = torch.Generator().manual_seed(3)
+    for dim in (7, 6):
+        for noise in (0.3, 0.03):
+            shape = (10, 24, 13, dim)
+            pred = torch.randn(shape, generator=g)
+            gt = pred + noise * torch.randn(shape, generator=g)
+            if dim == 7:
+                gt[..., 3:] = gt[..., 3:] / gt[..., 3:].norm(dim=-1, keepdim=True)
+            w = torch.rand(shape[:-1], generator=g)
+            n = pred.numel() // dim
+
+            def torch_grads(dt):
+                p = pred.to(dt).clone().requires_grad_(True)
+                l = im.se3_loss_torch(p, gt.to(dt))
+                (l * w.to(dt)).sum().backward()
+                return l.detach().double().numpy().reshape(n), p.grad.double().numpy().reshape(n, dim)
+
+            l64, g64 = torch_grads(torch.float64)
+            l32, g32 = torch_grads(torch.float32)
+            P, G, W = pred.numpy().reshape(n, dim).copy(), gt.numpy().reshape(n, dim).copy(), w.numpy().reshape(n).copy()
+            loss, ap = np.zeros(n, np.float32), np.zeros((n, dim), np.float32)
+            vp = lambda a: a.ctypes.data_as(C.c_void_p)
+            lib.ppr_cpu_se3_loss_f32(C.c_int64(n), dim, vp(P), vp(G), C.c_float(0.1), vp(loss), vp(W), vp(ap), None)
+            rp, rg = pred.double()[..., 3:], gt.double()[..., 3:]
+            if dim == 6:
+                rp, rg = im.axis_angle_to_quat(rp), im.axis_angle_to_quat(rg)
+            cos = ((im.quat_to_matrix(rp) * im.quat_to_matrix(rg)).sum((-1, -2)) - 1) / 2
+            ok = (~((cos - (1 - 1e-4)).abs() < 5e-6)).reshape(n).numpy()
+            scale = np.abs(g64).max()
+            err_fused = np.abs(ap.astype(np.float64) - g64)[ok].max() / scale
+            err_torch = np.abs(g32 - g64)[ok].max() / scale
+            assert err_fused < 1e-5 and err_fused <= err_torch, (dim, noise, err_fused, err_torch)
+            assert np.abs(loss.astype(np.float64) - l64)[ok].max() <= max(np.abs(l32 - l64)[ok].max(), 5e-7)
