@@ -159,6 +159,18 @@ int ppr_se3_loss_forward(int64_t n, int32_t dim, const float* pred, const float*
 int ppr_se3_loss_backward(int64_t n, int32_t dim, const float* pred, const float* gt, float rot_ratio,
                           const float* adj_loss, float* adj_pred, float* adj_gt, void* stream);
 
+/* ---- batch-input frame composition (replaces rotate_frame + compose_delta, dp_utils.py:60-72,
+ * 21-30, inside get_batch_input, dp_model.py:611-662) -------------------------------------------------------------
+ * n time samples: target[i] = T(global_q) @ T(q[i]);  queried[i] = T(delta[i]) @ target[i], delta = (xyz, axis-angle).
+ * global_q [7] (DEVICE), q [n,7], delta [n,6] -> target [n,7], queried [n,7].
+ * backward: adj_global [n,7] holds the PER-SAMPLE gradient w.r.t. global_q (the caller sums over n), adj_delta [n,6];
+ * both OVERWRITTEN.  q carries no gradient (mocap data). */
+int ppr_frame_compose_forward(int64_t n, const float* global_q, const float* q, const float* delta, float* target,
+                              float* queried, void* stream);
+int ppr_frame_compose_backward(int64_t n, const float* global_q, const float* q, const float* delta,
+                               const float* adj_target, const float* adj_queried, float* adj_global, float* adj_delta,
+                               void* stream);
+
 /* Number of kernels the library has launched since load (bench.py's gpu_launches). */
 int64_t ppr_launch_count(void);
 

@@ -20,6 +20,7 @@
 #include "../../include/ppr_b200.h"
 #include "../../ppr_diffphys_b200/csrc/ppr_body.h"
 #include "../../ppr_diffphys_b200/csrc/ppr_loss.h"
+#include "../../ppr_diffphys_b200/csrc/ppr_frame.h"
 
 using namespace ppr;
 
@@ -364,6 +365,17 @@ PPR_CPU_API(f64, double)
     }
 PPR_CPU_SE3(f64, double)
 PPR_CPU_SE3(f32, float)
+
+// batch-input frame composition + adjoint in float64 (ppr_frame.h), checked against torch autograd on the CPU
+extern "C" int ppr_cpu_frame_compose_f64(int64_t n, const double* gq, const double* q, const double* d, double* target,
+                                         double* queried, const double* at, const double* aq, double* adj_g,
+                                         double* adj_d) {
+    for (int64_t i = 0; i < n; ++i) {
+        ppr::frame_compose<double>(gq, q + 7 * i, d + 6 * i, target + 7 * i, queried + 7 * i);
+        if (at) ppr::frame_compose_adj<double>(gq, q + 7 * i, d + 6 * i, at + 7 * i, aq + 7 * i, adj_g + 7 * i, adj_d + 6 * i);
+    }
+    return 0;
+}
 
 extern "C" int ppr_cpu_num_threads(void) {
 #ifdef _OPENMP

@@ -18,7 +18,7 @@ EXPORTS = [
     "ppr_model_set_gravity", "ppr_model_set_checkpoint_every", "ppr_model_set_latency_envs",
     "ppr_model_latency_envs", "ppr_model_envs_per_group", "ppr_model_group_threads", "ppr_fk_forward", "ppr_fk_backward",
     "ppr_rollout_workspace_bytes", "ppr_rollout_forward", "ppr_rollout_backward", "ppr_se3_loss_forward",
-    "ppr_se3_loss_backward", "ppr_launch_count",
+    "ppr_se3_loss_backward", "ppr_frame_compose_forward", "ppr_frame_compose_backward", "ppr_launch_count",
 ]
 
 
@@ -35,6 +35,8 @@ def _declare(lib):
     lib.ppr_model_set_attach.argtypes = [_vp, _f32, _f32]
     lib.ppr_model_set_gravity.argtypes = [_vp, C.POINTER(C.c_float)]
     lib.ppr_model_set_checkpoint_every.argtypes = [_vp, C.c_int32]
+    lib.ppr_frame_compose_forward.argtypes = [_i64, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.ppr_frame_compose_backward.argtypes = [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     lib.ppr_se3_loss_forward.argtypes = [_i64, C.c_int32, _vp, _vp, _f32, _vp, _vp]
     lib.ppr_se3_loss_backward.argtypes = [_i64, C.c_int32, _vp, _vp, _f32, _vp, _vp, _vp, _vp]
     lib.ppr_model_set_joint_X_p_env.argtypes = [_vp, _vp, _i64]

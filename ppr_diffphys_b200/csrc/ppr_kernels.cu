@@ -28,6 +28,7 @@
 #include "../../include/ppr_b200.h"
 #include "ppr_body.h"
 #include "ppr_loss.h"
+#include "ppr_frame.h"
 
 using namespace ppr;
 typedef V3<float> F3;
@@ -1650,6 +1651,53 @@ extern "C" int ppr_se3_loss_backward(int64_t n, int32_t dim, const float* pred, 
     if (n == 0) return 0;
     se3_loss_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         n, dim, pred, gt, rot_ratio, 1e-4f, adj_loss, adj_pred, adj_gt);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------- frame composition
+// One thread per time sample; see ppr_frame.h.
+__global__ void __launch_bounds__(256)
+frame_compose_forward_kernel(int64_t n, const float* __restrict__ gq, const float* __restrict__ q,
+                             const float* __restrict__ d, float* __restrict__ target, float* __restrict__ queried) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float g[7], qi[7], di[6], t[7], u[7];
+    for (int k = 0; k < 7; ++k) { g[k] = gq[k]; qi[k] = q[i * 7 + k]; }
+    for (int k = 0; k < 6; ++k) di[k] = d[i * 6 + k];
+    frame_compose<float>(g, qi, di, t, u);
+    for (int k = 0; k < 7; ++k) { target[i * 7 + k] = t[k]; queried[i * 7 + k] = u[k]; }
+}
+__global__ void __launch_bounds__(256)
+frame_compose_backward_kernel(int64_t n, const float* __restrict__ gq, const float* __restrict__ q,
+                              const float* __restrict__ d, const float* __restrict__ at, const float* __restrict__ aq,
+                              float* __restrict__ adj_g, float* __restrict__ adj_d) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float g[7], qi[7], di[6], a[7], b[7], og[7], od[6];
+    for (int k = 0; k < 7; ++k) { g[k] = gq[k]; qi[k] = q[i * 7 + k]; a[k] = at[i * 7 + k]; b[k] = aq[i * 7 + k]; }
+    for (int k = 0; k < 6; ++k) di[k] = d[i * 6 + k];
+    frame_compose_adj<float>(g, qi, di, a, b, og, od);
+    for (int k = 0; k < 7; ++k) adj_g[i * 7 + k] = nan0(og[k]);
+    for (int k = 0; k < 6; ++k) adj_d[i * 6 + k] = nan0(od[k]);
+}
+
+extern "C" int ppr_frame_compose_forward(int64_t n, const float* global_q, const float* q, const float* delta,
+                                         float* target, float* queried, void* stream) {
+    if (n < 0 || !global_q || !q || !delta || !target || !queried) return PPR_E_ARG;
+    if (n == 0) return 0;
+    frame_compose_forward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, global_q, q, delta,
+                                                                                              target, queried);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+extern "C" int ppr_frame_compose_backward(int64_t n, const float* global_q, const float* q, const float* delta,
+                                          const float* adj_target, const float* adj_queried, float* adj_global,
+                                          float* adj_delta, void* stream) {
+    if (n < 0 || !global_q || !q || !delta || !adj_target || !adj_queried || !adj_global || !adj_delta) return PPR_E_ARG;
+    if (n == 0) return 0;
+    frame_compose_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n, global_q, q, delta, adj_target, adj_queried, adj_global, adj_delta);
     g_launches++;
     return (int)cudaGetLastError();
 }

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from .model import ASSET_DIR, load_robot
-from .ops import ForwardKinematics, ForwardWarp, Se3Loss, SimEnv, convert_ppr_warp
+from .ops import ForwardKinematics, ForwardWarp, FrameCompose, Se3Loss, SimEnv, convert_ppr_warp
 
 
 # ----------------------------------------------------------------------------------------- geometry (torch, xyzw)
@@ -243,17 +243,17 @@ class ImitationModel(nn.Module):
 
     def get_batch_input(self, steps_fr):
         msm = self.get_mocap_data(steps_fr)
-        target_q = rotate_frame(self.global_q, torch.cat([msm["pos"], msm["orn"]], -1))      # bs,T,7
+        fid = steps_fr.reshape(-1)
+        bs, T = steps_fr.shape
+        delta_root = self.root_pose_mlp(fid).view(bs, T, 6)
+        # rotate_frame(global_q, .) then compose_delta(., delta_root): one fused kernel each way (ops.FrameCompose)
+        target_q, queried_q = FrameCompose.apply(self.global_q, torch.cat([msm["pos"], msm["orn"]], -1), delta_root)
         target_qd = rotate_frame_vel(self.global_q, torch.cat([msm["vel"], msm["avel"]], -1))  # bs,T,6
         f2s = slice(0, None, self.steps_per_fr_interval)   # == self.frame2step (evenly strided), as a view: no index tensor
         target_position, _, self.target_trajs = self.fk_pos_vel(target_q[:, f2s], msm["jang"][:, f2s],
                                                                 target_qd[:, f2s], msm["jvel"][:, f2s])
-        fid = steps_fr.reshape(-1)
-        bs, T = steps_fr.shape
-        delta_root = self.root_pose_mlp(fid).view(bs, T, 6)
         delta_ja = self.joint_angle_mlp(fid).view(bs, T, -1)
         queried_qd = self.vel_mlp(fid).view(bs, T, -1)
-        queried_q = compose_delta(target_q, delta_root)
         queried_ja = msm["jang"] + delta_ja
         # time-major flattening (rearrange_pred, :555-572)
         q_all = torch.cat([queried_q, queried_ja], -1).permute(1, 0, 2).reshape(T, -1)

@@ -375,3 +375,37 @@ class Se3Loss(torch.autograd.Function):
             _lib.check(_lib.lib().ppr_se3_loss_backward(n, dim, _ptr(p), _ptr(g), C.c_float(ctx.rot_ratio), _ptr(a),
                                                         _ptr(ap), _ptr(ag), _stream()), "ppr_se3_loss_backward")
         return (ap if ctx.needs_input_grad[0] else None), ag, None
+
+
+class FrameCompose(torch.autograd.Function):
+    """``FrameCompose.apply(global_q[7], q[...,7], delta[...,6]) -> (target[...,7], queried[...,7])`` --
+    ``rotate_frame(global_q, q)`` followed by ``compose_delta(target, delta)`` of the batch-input producer
+    (dp_utils.py:60-72,21-30 inside get_batch_input, dp_model.py:611-662) as one kernel forward and one backward
+    (SURVEY.md 8f rank 2).  Gradients flow to ``global_q`` and ``delta``; ``q`` (mocap data) gets none."""
+
+    @staticmethod
+    def forward(ctx, global_q, q, delta):
+        assert q.is_cuda and q.shape[-1] == 7 and delta.shape[-1] == 6 and q.shape[:-1] == delta.shape[:-1]
+        dev = q.device
+        g, qq, d = _f32c(global_q, dev), _f32c(q, dev), _f32c(delta, dev)
+        n = qq.numel() // 7
+        target, queried = torch.empty_like(qq), torch.empty_like(qq)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ppr_frame_compose_forward(n, _ptr(g), _ptr(qq), _ptr(d), _ptr(target), _ptr(queried),
+                                                            _stream()), "ppr_frame_compose_forward")
+        ctx.save_for_backward(g, qq, d)
+        return target, queried
+
+    @staticmethod
+    def backward(ctx, adj_target, adj_queried):
+        g, qq, d = ctx.saved_tensors
+        n = qq.numel() // 7
+        z = lambda a: torch.zeros_like(qq) if a is None else _f32c(a, qq.device)
+        at, aq = z(adj_target), z(adj_queried)
+        adj_g = torch.empty(n, 7, device=qq.device, dtype=torch.float32)
+        adj_d = torch.empty_like(d)
+        with torch.cuda.device(qq.device):
+            _lib.check(_lib.lib().ppr_frame_compose_backward(n, _ptr(g), _ptr(qq), _ptr(d), _ptr(at), _ptr(aq),
+                                                             _ptr(adj_g), _ptr(adj_d), _stream()),
+                       "ppr_frame_compose_backward")
+        return (adj_g.sum(0) if ctx.needs_input_grad[0] else None), None, (adj_d if ctx.needs_input_grad[2] else None)

@@ -132,3 +132,34 @@ def test_fused_se3_loss_matches_composed_torch_definition(dim, noise):
         assert err_fused < max(2e-4, 3 * err_torch), (err_fused, err_torch)
     with pytest.raises(RuntimeError):
         se3_loss(pred, gt)                                         # CPU tensors: no CPU path
+
+
+def test_fused_frame_compose_matches_composed_torch_functions():
+    """ops.FrameCompose (2 launches) == rotate_frame + compose_delta + autograd on float32 CUDA tensors."""
+    from ppr_diffphys_b200 import FrameCompose, _lib
+    from ppr_diffphys_b200.imitation import compose_delta, rotate_frame
+    g = torch.Generator().manual_seed(5)
+    bs, T = 10, 760
+    q = torch.randn(bs, T, 7, generator=g)
+    q[..., 3:] = q[..., 3:] / q[..., 3:].norm(dim=-1, keepdim=True)
+    d0 = torch.randn(bs, T, 6, generator=g) * 0.2
+    d0[0, :4, 3:] = 0
+    wt = torch.randn(bs, T, 7, generator=g).cuda()
+    wu = torch.randn(bs, T, 7, generator=g).cuda()
+    out = []
+    for fused in (False, True):
+        gq = torch.tensor([0.1, 0.4, -0.3, 0.05, -0.1, 0.2, 0.9], device="cuda", requires_grad=True)
+        d = d0.clone().cuda().requires_grad_(True)
+        n0 = _lib.launch_count()
+        if fused:
+            t, u = FrameCompose.apply(gq, q.cuda(), d)
+        else:
+            t = rotate_frame(gq, q.cuda())
+            u = compose_delta(t, d)
+        ((t * wt).sum() + (u * wu).sum()).backward()
+        out.append((t.detach(), u.detach(), gq.grad, d.grad, _lib.launch_count() - n0))
+    assert out[1][4] == 2 and out[0][4] == 0
+    assert torch.allclose(out[0][0], out[1][0], atol=2e-6) and torch.allclose(out[0][1], out[1][1], atol=4e-6)
+    assert torch.allclose(out[0][2], out[1][2], rtol=2e-4, atol=1e-2)      # sums of 7600 float32 terms
+    assert torch.isfinite(out[1][3]).all()
+    assert float((out[0][3] - out[1][3]).abs().max() / out[0][3].abs().max()) < 1e-5

@@ -171,3 +171,34 @@ def test_se3_loss_float32_accuracy_beats_trace_form():
             err_torch = np.abs(g32 - g64)[ok].max() / scale
             assert err_fused < 1e-5 and err_fused <= err_torch, (dim, noise, err_fused, err_torch)
             assert np.abs(loss.astype(np.float64) - l64)[ok].max() <= max(np.abs(l32 - l64)[ok].max(), 5e-7)
+
+
+def test_frame_compose_adjoint_f64_equals_autograd():
+    """ppr_frame.h (rotate_frame + compose_delta of the batch-input producer and their hand-written adjoint, what the
+    CUDA kernels instantiate in float32) in float64 == the composed torch functions + autograd, including zero and
+    tiny axis-angle deltas and an un-normalised global quaternion."""
+    import ctypes as C
+    from oracle import cpu_port
+    lib = cpu_port.lib()
+    g = torch.Generator().manual_seed(0)
+    n = 200
+    gq = torch.tensor([0.1, 0.2, -0.3, 0.05, -0.1, 0.2, 1.1], dtype=torch.float64, requires_grad=True)
+    q = torch.randn(n, 7, generator=g, dtype=torch.float64)
+    q[:, 3:] /= q[:, 3:].norm(dim=-1, keepdim=True)
+    d = torch.randn(n, 6, generator=g, dtype=torch.float64) * 0.3
+    d[:3, 3:] = 0
+    d[3:6, 3:] *= 1e-8
+    d.requires_grad_(True)
+    t = im.rotate_frame(gq, q)
+    u = im.compose_delta(t, d)
+    wt = torch.randn(n, 7, generator=g, dtype=torch.float64)
+    wu = torch.randn(n, 7, generator=g, dtype=torch.float64)
+    ((t * wt).sum() + (u * wu).sum()).backward()
+    T, U, ag, ad = np.zeros((n, 7)), np.zeros((n, 7)), np.zeros((n, 7)), np.zeros((n, 6))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    GQ, Q, D = gq.detach().numpy().copy(), q.numpy().copy(), d.detach().numpy().copy()
+    WT, WU = wt.numpy().copy(), wu.numpy().copy()
+    lib.ppr_cpu_frame_compose_f64(C.c_int64(n), vp(GQ), vp(Q), vp(D), vp(T), vp(U), vp(WT), vp(WU), vp(ag), vp(ad))
+    assert np.abs(T - t.detach().numpy()).max() < 1e-13 and np.abs(U - u.detach().numpy()).max() < 1e-13
+    assert np.abs(ag.sum(0) - gq.grad.numpy()).max() < 1e-11
+    assert np.abs(ad - d.grad.numpy()).max() < 1e-12
