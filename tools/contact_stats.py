@@ -45,7 +45,9 @@ def main():
         cnt = cnt.reshape(T - 1, ngroups, epg, rm.nb)
     print("workload %s, %d envs, packing %d threads / %d envs" % (wl, bs, threads, epg))
     print("mean active points per env-substep: %.2f" % cnt.sum(-1).mean())
-    print("per body mean:", np.round(cnt.mean((0, 1, 2)), 2))
+    # block layout: columns are POSITIONS in the block (the library orders the bodies to balance the contact-prone
+    # leaf meshes over the warps), not body indices
+    print("per body (block layout: per position) mean:", np.round(cnt.mean((0, 1, 2)), 2))
     print("per body max :", cnt.max((0, 1, 2)))
     nz = cnt[cnt > 0]
     print("bodies with contact per env-substep: %.2f; points per touching body: mean %.2f, p50 %d, p90 %d, p99 %d, max %d"
