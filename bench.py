@@ -96,10 +96,10 @@ def cpu_measure(robot, window, stride, target_seconds=12.0, steps=1, warmup=0):
     """Times the CPU port (oracle/cpu_port, OpenMP over envs, all host threads) on a bounded sample of the
     workload: bs_sample envs x `window` substeps, forward + reverse sweep. Returns env-steps/s."""
     import torch
-    from oracle.cpu_port import CpuRollout, num_threads
+    from oracle.cpu_port import CpuRollout, use_all_cores
     from ppr_diffphys_b200 import load_robot
     rm = load_robot(robot)
-    cores = num_threads()
+    cores = use_all_cores()
     nsteps = window + 1
     F = (nsteps - 1) // stride + 1
 

@@ -34,6 +34,16 @@ def num_threads():
     return int(lib().ppr_cpu_num_threads())
 
 
+def use_all_cores():
+    """Use every core this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().ppr_cpu_set_num_threads(int(n))
+    return num_threads()
+
+
 def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 

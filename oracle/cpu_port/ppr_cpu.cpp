@@ -377,6 +377,12 @@ extern "C" int ppr_cpu_frame_compose_f64(int64_t n, const double* gq, const doub
     return 0;
 }
 
+// torchrun exports OMP_NUM_THREADS=1 to its workers; the timed CPU baseline must still use every host core
+extern "C" void ppr_cpu_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
 extern "C" int ppr_cpu_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
