@@ -65,3 +65,16 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 code = "\n".join(l for l in txt.splitlines() if re.match(r"\s*(import|from|#include)\b", l))
                 assert "oracle" not in code, f
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/ppr_b200.h must compile as C99 (no C++ / torch types in the signatures)."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
+        f.write('#include "include/ppr_b200.h"\nint main(void) { ppr_model_desc d; (void)d; return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", root, f.name],
+                       capture_output=True, text=True)
+    os.unlink(f.name)
+    assert r.returncode == 0, r.stderr
