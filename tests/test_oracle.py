@@ -145,3 +145,25 @@ def test_autograd_matches_finite_differences(robot, height):
             fd = (f(*ap) - f(*am)) / (2 * h)
             an = (gr * v).sum()
             assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)) + 1e-7, (k, float(fd), float(an))
+
+
+@pytest.mark.parametrize("fixture", ["laikago", "laikago_air", "human", "quad"])
+def test_oracle_reproduces_committed_golden_vectors(fixture):
+    """The fixtures under tests/golden/ (what the GPU parity tests compare against) are exactly what the oracle
+    computes today: guards against silent drift of the oracle after the fixtures were frozen."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rollout_%s.npz" % fixture))
+    keys = ["q_init", "qd_init", "torques", "res_f", "refs", "target_ke", "target_kd", "body_inv_mass", "body_inertia",
+            "body_inv_inertia"]
+    m = so.OracleModel(load_robot(str(z["robot"])))
+    o = {k: torch.from_numpy(z["in_" + k]).double().requires_grad_(True) for k in keys}
+    pos, vel, grf, jaf = so.rollout(m, *[o[k] for k in keys], float(z["dt"]), int(z["stride"]), int(z["nframes"]))
+    assert (pos.detach() - torch.from_numpy(z["pos"])).abs().max() < 1e-12
+    assert (vel.detach() - torch.from_numpy(z["vel"])).abs().max() < 1e-11
+    assert (grf.detach() - torch.from_numpy(z["grf"])).abs().max() < 1e-9
+    assert (jaf.detach() - torch.from_numpy(z["jaf"])).abs().max() < 1e-9
+    loss = (pos * torch.from_numpy(z["adj_pos"])).sum() + (vel * torch.from_numpy(z["adj_vel"])).sum()
+    grads = torch.autograd.grad(loss, [o[k] for k in keys])
+    for k, g in zip(keys, grads):
+        ref = torch.from_numpy(z["grad_" + k])
+        assert (g - ref).norm() <= 1e-10 * ref.norm() + 1e-14, k
