@@ -78,3 +78,43 @@ def test_header_is_plain_c():
                        capture_output=True, text=True)
     os.unlink(f.name)
     assert r.returncode == 0, r.stderr
+
+
+def test_model_create_validates_before_touching_the_device():
+    """ppr_model_create rejects malformed articulations with the documented negative codes (validation runs before
+    any CUDA call, so this is checkable without a GPU), and a VALID description fails loudly -- a positive
+    cudaError_t, never a silent CPU model -- when no device exists."""
+    import copy
+    import numpy as np
+    import torch
+    from ppr_diffphys_b200 import _lib, load_robot
+    from ppr_diffphys_b200._capi import make_desc
+    lib = C.CDLL(_lib.LIB_PATH)
+    lib.ppr_model_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+
+    def create(rm):
+        d, keep = make_desc(rm)
+        h = C.c_void_p()
+        rc = lib.ppr_model_create(C.byref(d), C.byref(h))
+        return rc, h
+
+    base = load_robot("laikago")
+    assert lib.ppr_model_create(None, None) == -1                                   # PPR_E_ARG
+    bad = copy.deepcopy(base)
+    bad.joint_type = np.array(bad.joint_type).copy()
+    bad.joint_type[3] = 2                                                           # prismatic: not a joint of this path
+    assert create(bad)[0] == -2                                                     # PPR_E_SHAPE
+    bad = copy.deepcopy(base)
+    bad.joint_parent = np.array(bad.joint_parent).copy()
+    bad.joint_parent[2] = 5                                                         # parent after child
+    assert create(bad)[0] == -2
+    bad = copy.deepcopy(base)
+    bad.contact_body = np.array(bad.contact_body).copy()
+    bad.contact_body[0] = 99                                                        # contact on a body that does not exist
+    assert create(bad)[0] == -1
+    d, keep = make_desc(base)
+    d.nb = 33                                                                       # more bodies than a warp has lanes
+    assert lib.ppr_model_create(C.byref(d), C.byref(C.c_void_p())) == -2
+    if not torch.cuda.is_available():
+        rc, h = create(base)
+        assert rc > 0 and not h.value, rc                                           # cudaError_t, no handle
