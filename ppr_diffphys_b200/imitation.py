@@ -185,21 +185,20 @@ class ImitationModel(nn.Module):
         self.steps_per_fr_interval = int(self.frame_interval / self.dt)
         self.register_buffer("amp_info", torch.as_tensor(frames))
         self.register_buffer("bullet2gl", _BULLET2GL.clone(), persistent=False)
+        gl = torch.as_tensor(frames).clone()
+        P = _BULLET2GL
+        for a, b in ((0, 3), (3, 6), (31, 34), (34, 37)):     # pos, orn.xyz, vel, avel (parse_amp's column map)
+            gl[:, a:b] = gl[:, a:b] @ P.T
+        self.register_buffer("amp_gl", gl, persistent=False)
 
     def get_mocap_data(self, steps_fr):
         """linear interpolation / extrapolation of all columns at fractional frame ids (dp_model.py:421-427),
-        then bullet2gl (dp_utils.py:141-156, in_bullet = False)."""
+        then bullet2gl (dp_utils.py:141-156, in_bullet = False).  bullet2gl is linear and the same for every frame,
+        so it is applied ONCE to the clip (`amp_gl`, preset_data) and the per-iteration work is one gather + lerp."""
         f0 = steps_fr.floor().clamp(0, self.total_frames - 2).long()
         w = (steps_fr - f0.float())[..., None]
-        amp = self.amp_info[f0] * (1 - w) + self.amp_info[f0 + 1] * w
-        m = parse_amp(amp)
-        P = self.bullet2gl
-        out = dict(jang=m["jang"], jvel=m["jvel"])
-        out["pos"] = m["pos"] @ P.T
-        out["orn"] = torch.cat([m["orn"][..., :3] @ P.T, m["orn"][..., 3:]], -1)
-        out["vel"] = m["vel"] @ P.T
-        out["avel"] = m["avel"] @ P.T
-        return out
+        amp = torch.lerp(self.amp_gl[f0], self.amp_gl[f0 + 1], w)
+        return parse_amp(amp)
 
     def lowest_point(self, body_q):
         """min world-y over the collision vertices (stands in for get_foot_height's mesh query, :574-579)."""
@@ -248,7 +247,8 @@ class ImitationModel(nn.Module):
         delta_root = self.root_pose_mlp(fid).view(bs, T, 6)
         # rotate_frame(global_q, .) then compose_delta(., delta_root): one fused kernel each way (ops.FrameCompose)
         target_q, queried_q = FrameCompose.apply(self.global_q, torch.cat([msm["pos"], msm["orn"]], -1), delta_root)
-        target_qd = rotate_frame_vel(self.global_q, torch.cat([msm["vel"], msm["avel"]], -1))  # bs,T,6
+        # the target twists only feed the (unused) twist output of the target FK: no gradient path, none recorded
+        target_qd = rotate_frame_vel(self.global_q.detach(), torch.cat([msm["vel"], msm["avel"]], -1))  # bs,T,6
         f2s = slice(0, None, self.steps_per_fr_interval)   # == self.frame2step (evenly strided), as a view: no index tensor
         target_position, _, self.target_trajs = self.fk_pos_vel(target_q[:, f2s], msm["jang"][:, f2s],
                                                                 target_qd[:, f2s], msm["jvel"][:, f2s])
