@@ -141,9 +141,8 @@ PPR_HD void contact_point_adj(const Body<T>& b, const M3<T>& Rb, V3<T> xc, V3<T>
 // ------------------------------------------------------------------------------------------ joints (K4)
 template <class T>
 PPR_HD T joint_limit_force(T q, T qd, T lo, T hi, T lke, T lkd) {
-    T lim = T(0);
-    if (q < lo) lim = lke * (lo - q) - lkd * (qd < T(0) ? qd : T(0));
-    if (q > hi) lim = lke * (hi - q) - lkd * (qd > T(0) ? qd : T(0));
+    T lim = sel(q < lo, lke * (lo - q) - lkd * sel(qd < T(0), qd, T(0)), T(0));
+    lim = sel(q > hi, lke * (hi - q) - lkd * sel(qd > T(0), qd, T(0)), lim);
     return lim;
 }
 // adjoint of sc = ke(q-target) + kd qd + act - lim, given g = adj_sc
@@ -158,13 +157,10 @@ PPR_HD void joint_scalar_adj(T q, T qd, const JointCtl<T>& c, int k, T g, T& g_q
     adj_kd[k] += qd * g;
     if (!LIMITS) return;
     T g_lim = -g;
-    if (q > c.hi[k]) {
-        g_q += -c.lke[k] * g_lim;
-        if (qd > T(0)) g_qd += -c.lkd[k] * g_lim;
-    } else if (q < c.lo[k]) {
-        g_q += -c.lke[k] * g_lim;
-        if (qd < T(0)) g_qd += -c.lkd[k] * g_lim;
-    }
+    auto above = q > c.hi[k];
+    auto below = (q < c.lo[k]) && !above;
+    g_q += sel(above || below, -c.lke[k] * g_lim, T(0));
+    g_qd += sel((above && (qd > T(0))) || (below && (qd < T(0))), -c.lkd[k] * g_lim, T(0));
 }
 
 // Twist angle of r_err about `axis` (quat_twist + acos + sign, integrator_euler.py:235-241,398-400):
@@ -181,9 +177,9 @@ template <class T> PPR_HD void revolute_angle_adj(V3<T> axis, Q4<T> r_err, T g_q
     T la = sqrt(dot(axis, axis));
     T y = dot(axis, qvec(r_err)) * la;
     T den = y * y + r_err.w * r_err.w;
-    if (!(den > T(0))) return;
-    T g_y = T(2) * g_q * r_err.w / den;
-    g_rerr.w += -T(2) * g_q * y / den;
+    T iden = sel(den > T(0), T(1) / den, T(0));   // zero adjoint at the singular point
+    T g_y = T(2) * g_q * r_err.w * iden;
+    g_rerr.w += -T(2) * g_q * y * iden;
     T g_d = g_y * la;
     g_rerr.x += g_d * axis.x; g_rerr.y += g_d * axis.y; g_rerr.z += g_d * axis.z;
 }
@@ -219,8 +215,9 @@ template <class T> PPR_HD CompoundDec<T> compound_decompose(Q4<T> q_pc, const T*
         d.ang[2] = -atan2(d.c1x, d.c0x);
     }
     T rho = sqrt(d.c2.y * d.c2.y + d.c2.z * d.c2.z);
-    if (rho > T(0)) { T ir = T(1) / rho; d.ca0 = d.c2.z * ir; d.sa0 = -d.c2.y * ir; }
-    else { d.ca0 = T(1); d.sa0 = T(0); }  // atan2(0,0) = 0
+    T ir = T(1) / rho;
+    d.ca0 = sel(rho > T(0), d.c2.z * ir, T(1));   // atan2(0,0) = 0
+    d.sa0 = sel(rho > T(0), -d.c2.y * ir, T(0));
     d.sa1 = clampT(d.c2.x, T(-1), T(1));
     d.ca1 = sqrt(T(1) - d.sa1 * d.sa1);
     d.e1 = v3<T>(T(0), d.ca0, d.sa0);
@@ -236,10 +233,10 @@ template <class T> PPR_HD Q4<T> compound_decompose_adj(Q4<T> q_pc, const Compoun
     T g_phi = -g_ang[0], g_theta = -g_ang[1], g_psi = -g_ang[2];
     V3<T> g_c0 = vzero<T>(), g_c1 = vzero<T>(), g_c2 = vzero<T>();
     T den = d.c2.y * d.c2.y + d.c2.z * d.c2.z;
-    if (den > T(0)) { T id = T(1) / den; g_c2.y += g_phi * d.c2.z * id; g_c2.z -= g_phi * d.c2.y * id; }
+    { T id = sel(den > T(0), T(1) / den, T(0)); g_c2.y += g_phi * d.c2.z * id; g_c2.z -= g_phi * d.c2.y * id; }
     g_c2.x += -g_theta * safe_asin_adj(-d.c2.x);
     den = d.c1x * d.c1x + d.c0x * d.c0x;
-    if (den > T(0)) { T id = T(1) / den; g_c1.x += g_psi * d.c0x * id; g_c0.x -= g_psi * d.c1x * id; }
+    { T id = sel(den > T(0), T(1) / den, T(0)); g_c1.x += g_psi * d.c0x * id; g_c0.x -= g_psi * d.c1x * id; }
     return qrot_adj_q(q_pc, v3<T>(T(1), T(0), T(0)), g_c0) + qrot_adj_q(q_pc, v3<T>(T(0), T(1), T(0)), g_c1) +
            qrot_adj_q(q_pc, v3<T>(T(0), T(0), T(1)), g_c2);
 }
@@ -295,7 +292,7 @@ PPR_UNROLL
         // conditioned near the identity (see revolute_angle)
         V3<T> e = qvec(r_err);
         T l = sqrt(dot(e, e));
-        T inv = l > T(0) ? T(1) / l : T(0);
+        T inv = sel(l > T(0), T(1) / l, T(0));
         V3<T> ang_err = e * (inv * atan2(l, r_err.w) * T(2));
         f_out = x_err * ake + v_err * akd;
         t_out = qrot(qA, ang_err) * ake + w_err * (akd * ads);
@@ -439,7 +436,7 @@ PPR_UNROLL
     if (JM == JM_ALL && js.type == JT_FIXED) {
         V3<T> e = qvec(r_err);
         T l = sqrt(dot(e, e));
-        T inv = l > T(0) ? T(1) / l : T(0);
+        T inv = sel(l > T(0), T(1) / l, T(0));
         T ac = atan2(l, r_err.w) * T(2);
         V3<T> nrm = e * inv;
         V3<T> ang_err = nrm * ac;
@@ -455,13 +452,14 @@ PPR_UNROLL
         T g_ac = dot(nrm, g_ang);
         V3<T> g_n = g_ang * ac;
         T den = l * l + r_err.w * r_err.w;
-        if (l > T(0)) {
+        T iden = sel(den > T(0), T(1) / den, T(0));
+        {   // l = 0: inv = 0 and nrm = 0, every term below vanishes (zero adjoint at the singular point)
             T ng = dot(nrm, g_n);
-            T g_l = T(2) * g_ac * r_err.w / den;  // d(2 atan2(l, w))/dl
+            T g_l = T(2) * g_ac * r_err.w * iden;  // d(2 atan2(l, w))/dl
             g_rerr.x += (g_n.x - nrm.x * ng) * inv + nrm.x * g_l; g_rerr.y += (g_n.y - nrm.y * ng) * inv + nrm.y * g_l;
             g_rerr.z += (g_n.z - nrm.z * ng) * inv + nrm.z * g_l;
         }
-        if (den > T(0)) g_rerr.w += -T(2) * g_ac * l / den;
+        g_rerr.w += -T(2) * g_ac * l * iden;
         adjC.x += g_armc; adj_xcc -= g_armc;
         if (has_parent) { adj_xcp -= g_armp; }
         V3<T> g_xA = g_armp - g_xerr;
@@ -482,7 +480,7 @@ PPR_UNROLL
 template <class T>
 PPR_HD Body<T> integrate_fwd(const Body<T>& b, const M3<T>& Rb, V3<T> xc, V3<T> com, const Wrench<T>& F, T inv_m,
                              const T* I, const T* inv_I, V3<T> g, T dt) {
-    T nz = inv_m != T(0) ? T(1) : T(0);
+    T nz = sel(inv_m != T(0), T(1), T(0));
     V3<T> v1 = b.v + (F.f * inv_m + g * nz) * dt;
     V3<T> x1c = xc + v1 * dt;
     V3<T> wb = mrot_t(Rb, b.w);
@@ -508,7 +506,7 @@ PPR_HD void integrate_adj_core(const Body<T>& b, const M3<T>& Rb, V3<T> xc, V3<T
                                V3<T>& adj_xc, Wrench<T>& adjF, T& adj_inv_m, V3<T>& gI_a, V3<T>& gI_b, V3<T>& giI_a,
                                V3<T>& giI_b) {
     // ---- recompute
-    T nz = inv_m != T(0) ? T(1) : T(0);
+    T nz = sel(inv_m != T(0), T(1), T(0));
     V3<T> v1 = b.v + (F.f * inv_m + g * nz) * dt;
     V3<T> wb = mrot_t(Rb, b.w);
     V3<T> Iwb = matvec(I, wb);

@@ -26,6 +26,12 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float* out, const f
                                  ia[i] = (ia[i] ^ it) + i; ia[i] = (ia[i] & 0xffff) + u; }                    // 1 FFMA2 + same ALU
                 if (MODE == 4) { x[i].x = x[i].x * a; x[i].y = x[i].y + b; }                                  // FMUL + FADD
                 if (MODE == 5) { x[i] = __fmul2_rn(x[i], a2); x[i] = __fadd2_rn(x[i], b2); }                  // FMUL2 + FADD2
+                if (MODE == 6) { x[i] = __fmul2_rn(x[i], a2); }                                               // FMUL2
+                if (MODE == 7) { x[i] = __fadd2_rn(x[i], b2); }                                               // FADD2
+                if (MODE == 8) { x[i].x = x[i].x * a; x[i].y = x[i].y * a2.y; }                               // 2 FMUL
+                if (MODE == 9) { x[i].x = x[i].x + b; x[i].y = x[i].y + b2.y; }                               // 2 FADD
+                if (MODE == 10) { x[i] = __ffma2_rn(x[i], a2, x[(i + 1) % NCH]); }                            // FFMA2, 3 distinct regs
+                if (MODE == 11) { x[i].x = fmaf(x[i].x, a, x[(i + 1) % NCH].x); x[i].y = fmaf(x[i].y, a2.y, x[(i + 1) % NCH].y); }
             }
         }
     }
@@ -54,6 +60,12 @@ int main() {
     run<2>("2xFFMA + int ALU", 4, out, in);
     run<3>("1xFFMA2 + int ALU", 4, out, in);
     run<4>("FMUL + FADD", 2, out, in);
-    run<5>("FMUL2 + FADD2", 4, out, in);
+    run<5>("FMUL2 + FADD2 (fused)", 4, out, in);
+    run<6>("FMUL2", 2, out, in);
+    run<7>("FADD2", 2, out, in);
+    run<8>("2xFMUL", 2, out, in);
+    run<9>("2xFADD", 2, out, in);
+    run<10>("FFMA2 (3 varying operands)", 4, out, in);
+    run<11>("2xFFMA (3 varying operands)", 4, out, in);
     return 0;
 }
