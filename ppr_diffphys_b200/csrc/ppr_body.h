@@ -477,14 +477,23 @@ PPR_UNROLL
 }
 
 // ------------------------------------------------------------------------------------------ integrate (K5)
+// The part of K5 that does not depend on the wrench (body-frame angular velocity and the gyroscopic term): the CUDA
+// forward kernel evaluates it while it waits for the wrenches of the body's children.
+template <class T> struct IntegratePre { V3<T> wb, gyro; };
+template <class T> PPR_HD IntegratePre<T> integrate_pre(const Body<T>& b, const M3<T>& Rb, const T* I) {
+    IntegratePre<T> p;
+    p.wb = mrot_t(Rb, b.w);
+    p.gyro = cross(p.wb, matvec(I, p.wb));
+    return p;
+}
 template <class T>
-PPR_HD Body<T> integrate_fwd(const Body<T>& b, const M3<T>& Rb, V3<T> xc, V3<T> com, const Wrench<T>& F, T inv_m,
-                             const T* I, const T* inv_I, V3<T> g, T dt) {
+PPR_HD Body<T> integrate_post(const Body<T>& b, const M3<T>& Rb, V3<T> xc, V3<T> com, const Wrench<T>& F, T inv_m,
+                              const T* inv_I, V3<T> g, T dt, const IntegratePre<T>& pre) {
     T nz = sel(inv_m != T(0), T(1), T(0));
     V3<T> v1 = b.v + (F.f * inv_m + g * nz) * dt;
     V3<T> x1c = xc + v1 * dt;
-    V3<T> wb = mrot_t(Rb, b.w);
-    V3<T> tb = mrot_t(Rb, F.t) - cross(wb, matvec(I, wb));
+    V3<T> wb = pre.wb;
+    V3<T> tb = mrot_t(Rb, F.t) - pre.gyro;
     V3<T> w1 = mrot(Rb, wb + matvec(inv_I, tb) * dt);
     Q4<T> rq = b.r + qmul(q4<T>(w1.x, w1.y, w1.z, T(0)), b.r) * (T(0.5) * dt);
     T len;
@@ -495,6 +504,11 @@ PPR_HD Body<T> integrate_fwd(const Body<T>& b, const M3<T>& Rb, V3<T> xc, V3<T> 
     o.r = r1;
     o.x = x1c - qrot(r1, com);
     return o;
+}
+template <class T>
+PPR_HD Body<T> integrate_fwd(const Body<T>& b, const M3<T>& Rb, V3<T> xc, V3<T> com, const Wrench<T>& F, T inv_m,
+                             const T* I, const T* inv_I, V3<T> g, T dt) {
+    return integrate_post(b, Rb, xc, com, F, inv_m, inv_I, g, dt, integrate_pre(b, Rb, I));
 }
 
 // Core of K5^T. The inertia-parameter adjoints are rank-1 updates; they are returned as their factors

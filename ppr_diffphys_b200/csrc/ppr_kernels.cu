@@ -12,15 +12,18 @@
 // reference's atomic_add/sub at integrator_euler.py:179,449,451).  The time loop is inside the kernel: one launch
 // per rollout instead of the reference's 4 launches + 1 memset + 2 clones per substep (dp_model.py:1209-1228).
 // Per substep the forward kernel streams the state, the total body wrench, the active-contact record and the joint
-// angles (28 floats / body) to an HBM checkpoint buffer laid out [t][warp][component][lane] (128-byte coalesced
-// rows); the adjoint kernel streams it back in reverse (cp.async, one substep ahead) and recomputes every other
-// intermediate.
+// angles (24 floats / body for REVOLUTE-only robots, 28 otherwise) to an HBM checkpoint buffer laid out
+// [t][warp][quad][lane] as float4 quads: one STG.128 per quad, 512 contiguous bytes per warp instruction, and a lane
+// only ever touches its own quads; the adjoint kernel streams the rows back in reverse (one substep ahead, into
+// shared memory) and recomputes every other intermediate.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <new>
 #include <vector>
@@ -38,10 +41,17 @@ typedef Wrench<float> WrenchF;
 typedef M3<float> M3F;
 
 #define PPR_MAX_CHILD 8
-#define PPR_CKPT_FLOATS 28  // body_q 7 + body_qd 6 + total wrench 6 + active-contact record 5 (count, 8 x u16) +
-                           // joint angles 3 + pad 1 (rows stay a multiple of 32 x 16 bytes)
-#define PPR_REC_MAX 8
+// Checkpoint row of one body and substep = RQ float4 quads (quad q of lane l at float (q * 32 + l) * 4 of the warp's row):
+//   Q0 x.xyz r.x | Q1 r.yzw w.x | Q2 w.yz v.xy | Q3 v.z ang0 rec[0..1] | then
+//   RQ = 6 (REVOLUTE only): Q4 rec[2..3] F.t.xy | Q5 F.t.z F.f.xyz
+//   RQ = 7                : Q4 rec[2..3] ang1 ang2 | Q5 F.t.xyz F.f.x | Q6 F.f.yz - -
+// rec = active-contact record, 4 words = 8 halfwords: count, then up to PPR_REC_MAX point indices.
+template <int JM> struct RowOf { static constexpr int kQuads = JM == JM_REVOLUTE ? 6 : 7; };
+#define PPR_ROW_QUADS_MAX 7
+#define PPR_REC_MAX 7
 #define PPR_BLOCK 128  // FK kernels (warp layout)
+#define PPR_SUP_N 16   // cells per edge of a cube-map face of the support-function table
+#define PPR_SUP_FLOATS (6 * (PPR_SUP_N + 1) * (PPR_SUP_N + 1))
 #define PPR_CLIST_CAP 16  // penetrating points listed per body before falling back to the cooperative path
 #define PPR_CLIST_STRIDE (PPR_CLIST_CAP + 1)
 #ifndef PPR_BODY_MAJOR
@@ -70,6 +80,8 @@ struct DevModel {
     const int* cmat;          // [nc] material row
     const float4* mats;       // [nshape] ke kd kf mu
     const float* aabb;        // [nb,8] lo xyz, hi xyz, max dist, pad
+    const float* sup;         // support-function tables of the big bodies (PPR_SUP_FLOATS each), see support_lower_bound
+    const int* sup_of;        // [nb] table index of the body or -1
     float g[3], ake, akd;
     int mat_uniform;          // every contact uses material row cmat[0]
 };
@@ -115,13 +127,6 @@ __device__ __forceinline__ void cp_async16(volatile float* smem_dst, const float
     unsigned sa = (unsigned)__cvta_generic_to_shared((const void*)smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
 }
-// one checkpoint row of a warp = PPR_CKPT_FLOATS x 32 floats, contiguous in HBM: 6 x 16 B per lane
-__device__ __forceinline__ void cp_async_row(volatile float* smem_row, const float* grow, int lane) {
-#pragma unroll
-    for (int i = 0; i < PPR_CKPT_FLOATS * 32 / 4 / 32; ++i) cp_async16(smem_row + (i * 32 + lane) * 4, grow + (i * 32 + lane) * 4);
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // remove_nan of the reference (dp_utils.py:43-57, clip = False) applied at the store: NaN -> 0, everything else
 // (including +-inf) untouched. Saves one full pass over every gradient tensor on the host side.
 __device__ __forceinline__ float nan0(float v) { return v != v ? 0.f : v; }
@@ -157,6 +162,54 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #endif
     } while (!ok);
 }
+
+// TMA (bulk async copy engine): ONE elected lane moves a warp's whole checkpoint row (3 / 3.5 kB, contiguous in HBM) into
+// shared memory with a single instruction; completion is signalled on an mbarrier by byte count.  Replaces the six or
+// seven per-lane LDGSTS + commit/wait of the Ampere-style path (kept for the recompute instance, whose rows are written
+// by the same kernel through the generic proxy).
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(volatile float* smem_dst, const float* gsrc, unsigned bytes, unsigned long long* bar) {
+    unsigned d = (unsigned)__cvta_generic_to_shared((const void*)smem_dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+// Row stream of one warp of the adjoint kernel: issue() starts the copy of a row into the warp's buffer, wait() blocks
+// until the row issued last has landed.  BULK = TMA + mbarrier, else per-lane cp.async.
+template <int RQ, bool BULK> struct RowStream {
+    volatile float* buf;
+    unsigned long long* bar;
+    unsigned phase;
+    int lane;
+    __device__ __forceinline__ RowStream(volatile float* b, unsigned long long* m, int l) : buf(b), bar(m), phase(0), lane(l) {
+        if (BULK) {
+            if (lane == 0) {
+                mbar_init(bar, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncwarp();
+        }
+    }
+    __device__ __forceinline__ void issue(const float* grow) {
+        if (BULK) {
+            __syncwarp();   // every lane has read the previous row out of the buffer
+            if (lane == 0) {
+                mbar_expect_tx(bar, RQ * 512u);
+                bulk_load(buf, grow, RQ * 512u, bar);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < RQ; ++i) cp_async16(buf + (i * 32 + lane) * 4, grow + (i * 32 + lane) * 4);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    }
+    __device__ __forceinline__ void wait() {
+        if (BULK) { mbar_wait(bar, phase); phase ^= 1u; }
+        else asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+};
 
 // ----------------------------------------------------------------------------------------------- tree exchange
 // Collectives over the articulation tree, executed by EVERY thread of the group (warp or block):
@@ -309,7 +362,9 @@ template <int NT> struct BlockComm {
         P = get_body(ex, ps, xcp);
         wp = get_wrench(ex + 4 * NT, ps);
     }
-#ifdef PPR_MBAR_B   // barrier B as an mbarrier too (measured: its wait has no work to hide behind and only polls)
+#ifndef PPR_BAR_B_SYNC   // barrier B split-phase as well: the callers place the work that does not depend on the gathered
+                         // values (checkpoint stores, wrench-independent part of K5, own-body part of the pose adjoint)
+                         // between post_* and gather_*.  -DPPR_BAR_B_SYNC: plain hardware barrier (round-1 behaviour)
 #define PPR_ARRIVE_B() mbar_arrive(bar + 1)
 #define PPR_WAIT_B() do { mbar_wait(bar + 1, phB); phB ^= 1u; } while (0)
 #else
@@ -498,6 +553,30 @@ __device__ __forceinline__ ContactMat<float> mat_of(const DevModel& M, const Con
 //     compacted into the owner lane's list in shared memory -> returns their count, or -1 if more than
 //     PPR_CLIST_CAP penetrate (owner falls back to the cooperative evaluate-and-reduce path).
 // The test uses a 1e-6 m margin; the exact `c > 0` rejection of the reference is re-applied per point in phase B.
+//
+// Second-level cull of a big body: a lower bound of m(a) = min_k a . p_k (a = body-frame image of the ground normal,
+// the y-row of the rotation matrix) from a table of m sampled on a cube map of directions.  m is concave and positively
+// homogeneous, so for a = sum_i w_i n_i with w_i >= 0 (the bilinear weights of the four nodes of a's cell, which
+// reproduce the affine map (u, v) -> direction exactly) m(a) >= sum_i w_i m(n_i): the interpolated table value never
+// exceeds the height of the lowest vertex.  The AABB bound is centimetres loose for a rotated foot mesh that hovers
+// millimetres above the ground; this one is ~0.5 mm tight, so hovering feet skip the 96-vertex test.
+__device__ __forceinline__ float support_lower_bound(const float* __restrict__ T, float m0, float m1, float m2) {
+    const float ax = fabsf(m0), ay = fabsf(m1), az = fabsf(m2);
+    int face; float d, u, v;
+    if (ax >= ay && ax >= az) { face = m0 < 0.f ? 1 : 0; d = ax; u = m1; v = m2; }
+    else if (ay >= az) { face = m1 < 0.f ? 3 : 2; d = ay; u = m0; v = m2; }
+    else { face = m2 < 0.f ? 5 : 4; d = az; u = m0; v = m1; }
+    const float inv = 1.f / fmaxf(d, 1e-30f);
+    const float fu = fminf(fmaxf((u * inv + 1.f) * (0.5f * PPR_SUP_N), 0.f), (float)PPR_SUP_N);
+    const float fv = fminf(fmaxf((v * inv + 1.f) * (0.5f * PPR_SUP_N), 0.f), (float)PPR_SUP_N);
+    const int iu = min((int)fu, PPR_SUP_N - 1), iv = min((int)fv, PPR_SUP_N - 1);
+    const float wu = fu - (float)iu, wv = fv - (float)iv;   // in [0, 1]
+    const float* t = T + (face * (PPR_SUP_N + 1) + iv) * (PPR_SUP_N + 1) + iu;
+    const float t00 = t[0], t01 = t[1], t10 = t[PPR_SUP_N + 1], t11 = t[PPR_SUP_N + 2];
+    const float lo = (1.f - wv) * ((1.f - wu) * t00 + wu * t01) + wv * ((1.f - wu) * t10 + wu * t11);
+    return d * lo;
+}
+template <bool SUP>   // SUP: apply the support-function cull (forward pass; the adjoint's rare overflow path skips it)
 __device__ __forceinline__ int contact_candidates(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
                                                   const volatile float* st, int* __restrict__ clist, float& m0,
                                                   float& m1, float& m2) {
@@ -509,6 +588,14 @@ __device__ __forceinline__ int contact_candidates(const DevModel& M, const LaneI
                  fminf(m2 * st[(ST_AABB + 2) * 32 + b], m2 * st[(ST_AABB + 5) * 32 + b]) - st[(ST_AABB + 6) * 32 + b];
     bool maybe = L.valid && (L.c1 > L.c0) && !(ylow > 1e-6f);
     bool big = (L.c1 - L.c0) > M.big_threshold;
+#ifndef PPR_NO_SUPPORT_CULL
+    if (SUP && maybe && big) {   // (every big body has a table; the index is fetched here so that it costs no register)
+        // |rounding of the interpolation| << 1e-6 for bodies of < 1 m; the table itself is rounded down on the host
+        const float* T = M.sup + (size_t)M.sup_of[b] * PPR_SUP_FLOATS;
+        const float ysup = s.x.y + support_lower_bound(T, m0, m1, m2) - st[(ST_AABB + 6) * 32 + b];
+        maybe = !(ysup > 3e-6f);
+    }
+#endif
     int mine = (maybe && !big) ? -2 : 0;
     unsigned mask = __ballot_sync(FULL, maybe && big);
     if (mask == 0) return mine;
@@ -547,31 +634,69 @@ __device__ __forceinline__ int contact_candidates(const DevModel& M, const LaneI
 
 // record of the contact points that actually produced force in a substep (consumed by the adjoint kernel)
 struct ContactRec {
-    unsigned cnt;              // number of active points; > PPR_REC_MAX = not recorded (adjoint re-derives them)
-    unsigned long long lo, hi; // 8 x u16 point indices
+    unsigned long long lo, hi; // 8 halfwords: [0] = number of active points (> PPR_REC_MAX = not recorded, the adjoint
+                               // re-derives them), [1..7] = their indices
 };
+__device__ __forceinline__ unsigned rec_cnt(const ContactRec& r) { return (unsigned)r.lo & 0xffffu; }
+__device__ __forceinline__ void rec_overflow(ContactRec& r) { r.lo = (r.lo & ~0xffffull) | (unsigned long long)(PPR_REC_MAX + 1); }
 __device__ __forceinline__ void rec_push(ContactRec& r, int k) {
-    if (r.cnt < 4) r.lo |= (unsigned long long)(unsigned)k << (16 * r.cnt);
-    else if (r.cnt < 8) r.hi |= (unsigned long long)(unsigned)k << (16 * (r.cnt - 4));
-    r.cnt++;
+    const unsigned h = rec_cnt(r) + 1;   // halfword that takes the index
+    if (h < 4) r.lo |= (unsigned long long)(unsigned)k << (16 * h);
+    else if (h < 8) r.hi |= (unsigned long long)(unsigned)k << (16 * (h - 4));
+    if (h <= PPR_REC_MAX + 1) r.lo += 1ull;   // the count saturates at PPR_REC_MAX + 1
 }
 __device__ __forceinline__ int rec_get(const ContactRec& r, unsigned i) {
-    unsigned long long w = i < 4 ? r.lo : r.hi;
-    return (int)((w >> (16 * (i & 3))) & 0xffffull);
+    const unsigned h = i + 1;
+    unsigned long long w = h < 4 ? r.lo : r.hi;
+    return (int)((w >> (16 * (h & 3))) & 0xffffull);
+}
+// checkpoint row, part known BEFORE the child wrenches are gathered / part that needs the total wrench
+template <int RQ> __device__ __forceinline__ void row_store_pre(float4* c, const BodyF& s, const float* ang, const ContactRec& rec) {
+    c[0 * 32] = make_float4(s.x.x, s.x.y, s.x.z, s.r.x);
+    c[1 * 32] = make_float4(s.r.y, s.r.z, s.r.w, s.w.x);
+    c[2 * 32] = make_float4(s.w.y, s.w.z, s.v.x, s.v.y);
+    c[3 * 32] = make_float4(s.v.z, ang[0], __uint_as_float((unsigned)rec.lo), __uint_as_float((unsigned)(rec.lo >> 32)));
+    if (RQ == 7) c[4 * 32] = make_float4(__uint_as_float((unsigned)rec.hi), __uint_as_float((unsigned)(rec.hi >> 32)), ang[1], ang[2]);
+}
+template <int RQ> __device__ __forceinline__ void row_store_post(float4* c, const ContactRec& rec, const WrenchF& F) {
+    if (RQ == 6) {
+        c[4 * 32] = make_float4(__uint_as_float((unsigned)rec.hi), __uint_as_float((unsigned)(rec.hi >> 32)), F.t.x, F.t.y);
+        c[5 * 32] = make_float4(F.t.z, F.f.x, F.f.y, F.f.z);
+    } else {
+        c[5 * 32] = make_float4(F.t.x, F.t.y, F.t.z, F.f.x);
+        c[6 * 32] = make_float4(F.f.y, F.f.z, 0.f, 0.f);
+    }
+}
+// the same row read back from this lane's quads in shared memory
+template <int RQ> __device__ __forceinline__ void row_load(const float4* r, BodyF& s, WrenchF& F, ContactRec& rec, float* ang) {
+    const float4 a0 = lds128v(r), a1 = lds128v(r + 32), a2 = lds128v(r + 64), a3 = lds128v(r + 96), a4 = lds128v(r + 128),
+                 a5 = lds128v(r + 160);
+    s.x = v3<float>(a0.x, a0.y, a0.z); s.r = q4<float>(a0.w, a1.x, a1.y, a1.z);
+    s.w = v3<float>(a1.w, a2.x, a2.y); s.v = v3<float>(a2.z, a2.w, a3.x);
+    ang[0] = a3.y;
+    rec.lo = (unsigned long long)__float_as_uint(a3.z) | ((unsigned long long)__float_as_uint(a3.w) << 32);
+    rec.hi = (unsigned long long)__float_as_uint(a4.x) | ((unsigned long long)__float_as_uint(a4.y) << 32);
+    if (RQ == 6) {
+        ang[1] = 0.f; ang[2] = 0.f;
+        F.t = v3<float>(a4.z, a4.w, a5.x); F.f = v3<float>(a5.y, a5.z, a5.w);
+    } else {
+        const float4 a6 = lds128v(r + 192);
+        ang[1] = a4.z; ang[2] = a4.w;
+        F.t = v3<float>(a5.x, a5.y, a5.z); F.f = v3<float>(a5.w, a6.x, a6.y);
+    }
 }
 
-// K3 for the whole warp: subtracts contact wrenches from F (per lane = per body)
-__device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
-                                                  const M3F& Rb, F3 xc, const ContactMat<float>& cm0, const volatile float* st,
-                                                  int* __restrict__ clist, WrenchF& F, ContactRec& rec) {
+// K3 for the whole warp in two phases (they sit on different sides of the state rendezvous in the forward kernel):
+//   warp_contacts_search: which points penetrate (needs only this warp's body states)  -> cand / pen
+//   warp_contacts_eval  : subtracts their contact wrenches from F (per lane = per body) and records the active ones
+__device__ __forceinline__ int warp_contacts_search(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
+                                                    const volatile float* st, int* __restrict__ clist, unsigned& pen) {
     float m0, m1, m2;
-    int cand = contact_candidates(M, L, lane, s, st, clist, m0, m1, m2);
-    rec.cnt = 0; rec.lo = 0ull; rec.hi = 0ull;
-    const bool can_rec = M.nc <= 65535;
+    int cand = contact_candidates<true>(M, L, lane, s, st, clist, m0, m1, m2);
+    pen = 0;
     if (cand == -2) {
-        // small body (<= big_threshold <= 32 points, e.g. 8 box corners): pass 1 tests all points with four loads in
-        // flight and builds a bitmask, pass 2 evaluates only the penetrating ones (one inlined copy of the force code)
-        unsigned pen = 0;
+        // small body (<= big_threshold <= 32 points, e.g. 8 box corners): test all points with four loads in flight and
+        // build a bitmask; the evaluation phase visits only the penetrating ones (one inlined copy of the force code)
         for (int k0 = L.c0; k0 < L.c1; k0 += 4) {
             float4 p[4];
 #pragma unroll
@@ -580,6 +705,15 @@ __device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneI
             for (int u = 0; u < 4; ++u)
                 if (!(s.x.y + m0 * p[u].x + m1 * p[u].y + m2 * p[u].z - p[u].w > 1e-6f)) pen |= 1u << (k0 - L.c0 + u);
         }
+    }
+    return cand;
+}
+__device__ __forceinline__ void warp_contacts_eval(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
+                                                   const M3F& Rb, F3 xc, const ContactMat<float>& cm0, int cand, unsigned pen,
+                                                   int* __restrict__ clist, WrenchF& F, ContactRec& rec) {
+    rec.lo = 0ull; rec.hi = 0ull;
+    const bool can_rec = M.nc <= 65535;
+    if (cand == -2) {
         while (pen) {
             int k = L.c0 + __ffs(pen) - 1;
             pen &= pen - 1;
@@ -593,7 +727,7 @@ __device__ __forceinline__ void warp_contacts_fwd(const DevModel& M, const LaneI
             if (contact_point_fwd(s, Rb, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), F)) rec_push(rec, k);
         }
     }
-    if (cand == -1 || !can_rec) rec.cnt = PPR_REC_MAX + 1;
+    if (cand == -1 || !can_rec) rec_overflow(rec);
     unsigned mask = __ballot_sync(FULL, cand == -1);
     while (mask) {  // many penetrating points: evaluate cooperatively and reduce
         int a = __ffs(mask) - 1;
@@ -621,9 +755,10 @@ __device__ __forceinline__ void warp_contacts_adj(const DevModel& M, const LaneI
                                                   const volatile float* st, int* __restrict__ clist,
                                                   const ContactRec& rec, const WrenchF& adjF, BodyF& adjS, M3F& G,
                                                   F3& adj_xc) {
-    const bool ovf = L.valid && rec.cnt > PPR_REC_MAX;
+    const unsigned nrec = rec_cnt(rec);
+    const bool ovf = L.valid && nrec > PPR_REC_MAX;
     if (!ovf && L.valid) {
-        for (unsigned i = 0; i < rec.cnt; ++i) {
+        for (unsigned i = 0; i < nrec; ++i) {
             int k = rec_get(rec, i);
             float4 p = M.cpt[k];
             contact_point_adj(s, Rb, xc, v3<float>(p.x, p.y, p.z), p.w, mat_of(M, cm0, k), adjF, adjS, G, adj_xc);
@@ -631,7 +766,7 @@ __device__ __forceinline__ void warp_contacts_adj(const DevModel& M, const LaneI
     }
     if (!__any_sync(FULL, ovf)) return;
     float m0, m1, m2;
-    int cand = contact_candidates(M, L, lane, s, st, clist, m0, m1, m2);
+    int cand = contact_candidates<false>(M, L, lane, s, st, clist, m0, m1, m2);
     if (!ovf) cand = 0;
     if (cand == -2) {
         for (int k = L.c0; k < L.c1; ++k) {
@@ -792,21 +927,18 @@ __device__ __forceinline__ void store_wrench_row(float* base, const WrenchF& w) 
     base[0] = w.t.x; base[1] = w.t.y; base[2] = w.t.z; base[3] = w.f.x; base[4] = w.f.y; base[5] = w.f.z;
 }
 
-// forces of one substep; F = total wrench on this lane's body. Optionally exports the grf / jaf side channels.
+// Forces of one substep in two halves.  forces_pre: contacts + this body's joint, ends by PUBLISHING the wrench the
+// joint exerts on the parent; forces_post: adds the wrenches of the body's children -> F = total wrench on this lane's
+// body.  Work that does not need the children's wrenches goes between the two (split-phase rendezvous).
+// Optionally exports the grf / jaf side channels.
 template <int JM, bool LIMITS, bool QOFF, class Comm>
-__device__ __forceinline__ void warp_forces(Comm& comm, const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
-                                            const M3F& Rb, F3 xc, const JointCtl<float>& ctl, const ContactMat<float>& cm0,
-                                            const volatile float* st, const float4* xpq, int* clist, const float* res_f_row,
-                                            float* grf_row, float* jaf_row, WrenchF& F, ContactRec& rec, float* ang) {
-    comm.post_state(s, xc);   // published before the (long, warp-dependent) contact pass, awaited after it
-    F = wrench_zero<float>();
-    if (res_f_row && L.valid) {
-        F.t = v3<float>(res_f_row[0], res_f_row[1], res_f_row[2]);
-        F.f = v3<float>(res_f_row[3], res_f_row[4], res_f_row[5]);
-    }
-    warp_contacts_fwd(M, L, lane, s, Rb, xc, cm0, st, clist, F, rec);
-    WrenchF G = F;
-    if (grf_row && L.valid) store_wrench_row(grf_row, F);
+__device__ __forceinline__ WrenchF forces_pre(Comm& comm, const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
+                                              const M3F& Rb, F3 xc, const JointCtl<float>& ctl, const ContactMat<float>& cm0,
+                                              const volatile float* st, const float4* xpq, int* clist, const float* res_f_row,
+                                              float* grf_row, WrenchF& F, WrenchF& G, ContactRec& rec, float* ang) {
+    comm.post_state(s, xc);   // published before the (warp-dependent) contact search, awaited after it
+    unsigned pen;
+    const int cand = warp_contacts_search(M, L, lane, s, st, clist, pen);
     // joints: this lane is the child of its joint
     BodyF P;
     F3 xcp;
@@ -816,11 +948,29 @@ __device__ __forceinline__ void warp_forces(Comm& comm, const DevModel& M, const
     joint_fwd<float, JM, LIMITS, QOFF>(st_joint<Comm::kThreads, QOFF>(st, xpq, L.body, L.type), ctl, M.ake, M.akd, P, xcp, L.has_parent, s,
                                        Rb, xc, t, f, ap, ac, ang);
     WrenchF Wp = wrench_zero<float>();
-    if (L.type != JT_FREE) {
-        F.t -= t + cross(ac, f); F.f -= f;
-        if (L.has_parent) { Wp.t = t + cross(ap, f); Wp.f = f; }
-    }
+    if (L.type != JT_FREE && L.has_parent) { Wp.t = t + cross(ap, f); Wp.f = f; }
+#ifndef PPR_CONTACTS_EARLY
+    // The wrench on the parent does not depend on this body's contacts: publish it FIRST, so that the parent is not held
+    // up by the evaluation of the contact points (split-phase rendezvous B; the evaluation overlaps its skew).
     comm.post_wrench(Wp);
+#endif
+    F = wrench_zero<float>();
+    if (res_f_row && L.valid) {
+        F.t = v3<float>(res_f_row[0], res_f_row[1], res_f_row[2]);
+        F.f = v3<float>(res_f_row[3], res_f_row[4], res_f_row[5]);
+    }
+    warp_contacts_eval(M, L, lane, s, Rb, xc, cm0, cand, pen, clist, F, rec);
+    G = F;
+    if (grf_row && L.valid) store_wrench_row(grf_row, F);
+    if (L.type != JT_FREE) { F.t -= t + cross(ac, f); F.f -= f; }
+#ifdef PPR_CONTACTS_EARLY
+    comm.post_wrench(Wp);
+#endif
+    return Wp;
+}
+template <class Comm>
+__device__ __forceinline__ void forces_post(Comm& comm, const LaneInfo& L, const WrenchF& Wp, const WrenchF& G,
+                                            float* jaf_row, WrenchF& F) {
     comm.gather_wrench(Wp, L.child, L.maxc_w, F);
     if (jaf_row && L.valid) {
         WrenchF J; J.t = F.t - G.t; J.f = F.f - G.f;
@@ -830,22 +980,30 @@ __device__ __forceinline__ void warp_forces(Comm& comm, const DevModel& M, const
 
 // Resident blocks per SM asked of ptxas: forward <= 128 registers/thread, adjoint <= 168. Measured on B200
 // (profiles/README.md): issue-slot utilisation rises with resident warps; going further costs spills.
-#define PPR_FWD_MINB(NT) (512 / (NT))
-#define PPR_BWD_MINB(NT) (390 / (NT))
+#ifndef PPR_FWD_THREADS_PER_SM
+#define PPR_FWD_THREADS_PER_SM 512
+#endif
+#ifndef PPR_BWD_THREADS_PER_SM
+#define PPR_BWD_THREADS_PER_SM 390
+#endif
+#define PPR_FWD_MINB(NT) (PPR_FWD_THREADS_PER_SM / (NT))
+#define PPR_BWD_MINB(NT) (PPR_BWD_THREADS_PER_SM / (NT))
 
 // dynamic shared-memory layout (floats): [rows (adjoint only)] [static table] [params] [acc (adjoint only)] [clist] [comm]
 template <class Comm, bool ADJ> struct SmemLayout {
     static constexpr int NT = Comm::kThreads, NW = NT / 32;
     static constexpr int row = 0;
-    static constexpr int st = row + (ADJ ? NW * PPR_CKPT_FLOATS * 32 : 0);
+    static constexpr int st = row + (ADJ ? NW * PPR_ROW_QUADS_MAX * 4 * 32 : 0);
     static constexpr int par = st + PPR_NSTATIC * 32;
     static constexpr int xpq = par + PPR_NPAR * NT;
     static constexpr int acc = xpq + 8 * NT;
     static constexpr int clist = acc + (ADJ ? 20 * NT : 0);
     static constexpr int comm = clist + NW * 32 * PPR_CLIST_STRIDE;
-    static constexpr int total = comm + Comm::kExFloats;
+    static constexpr int rowbar = comm + Comm::kExFloats + ((Comm::kExFloats & 1) ? 1 : 0);   // NW 8-byte mbarriers
+    static constexpr int total = rowbar + (ADJ ? 2 * NW : 0);
     static constexpr size_t bytes = (size_t)total * sizeof(float);
     static_assert(comm % 4 == 0 && par % 4 == 0 && acc % 4 == 0, "float4 areas must be 16-byte aligned");
+    static_assert(rowbar % 2 == 0, "mbarriers must be 8-byte aligned");
 };
 
 template <class Comm, int JM, bool LIMITS, bool QOFF>
@@ -892,8 +1050,9 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     }
     __syncthreads();  // the static table is per block (all warps stage identical values)
 
-    float* ck = A.ckpt + (warp * PPR_CKPT_FLOATS) * 32 + lane;
-    const int64_t ck_step = A.nwarps * PPR_CKPT_FLOATS * 32;
+    constexpr int RQ = RowOf<JM>::kQuads;
+    float4* ck = (float4*)A.ckpt + (warp * RQ) * 32 + lane;
+    const int64_t ck_step = A.nwarps * RQ * 32;   // in float4
     // frame / checkpoint phases are carried as counters (no 64-bit divisions inside the time loop)
     int64_t fi = -1, fphase = 0, kphase = 0;
     for (int64_t t = 0; t < A.nsteps; ++t) {
@@ -914,35 +1073,25 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
         const M3F Rb = qmat(s.r);
         F3 xc = s.x + mrot(Rb, com);
         load_ctl(M, L, A, t, ke, kd, ctl);
-        WrenchF F;
+        WrenchF F, Fg;
         ContactRec rec;
         float ang[3];
-        warp_forces<JM, LIMITS, QOFF>(comm, M, L, lane, s, Rb, xc, ctl, cm0, st, xpq, clist, A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
-                    (frame && A.out_grf) ? A.out_grf + frow * 6 : nullptr,
-                    (frame && A.out_jaf) ? A.out_jaf + frow * 6 : nullptr, F, rec, ang);
-        // checkpoint (coalesced: component-major rows of 32 lanes), every K-th substep
+        const WrenchF Wp = forces_pre<JM, LIMITS, QOFF>(comm, M, L, lane, s, Rb, xc, ctl, cm0, st, xpq, clist,
+                    A.res_f ? A.res_f + ((t * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
+                    (frame && A.out_grf) ? A.out_grf + frow * 6 : nullptr, F, Fg, rec, ang);
+        // ---- between publishing the parent wrench and gathering the children's: everything that does not need them
+        // checkpoint (every K-th substep): state, joint angles, contact record
         const bool keep = kphase == 0;
         if (++kphase == A.ckpt_every) kphase = 0;
-        if (keep) {
-        float* c = ck;
-        ck += ck_step;
-        c[0 * 32] = s.x.x; c[1 * 32] = s.x.y; c[2 * 32] = s.x.z;
-        c[3 * 32] = s.r.x; c[4 * 32] = s.r.y; c[5 * 32] = s.r.z; c[6 * 32] = s.r.w;
-        c[7 * 32] = s.w.x; c[8 * 32] = s.w.y; c[9 * 32] = s.w.z;
-        c[10 * 32] = s.v.x; c[11 * 32] = s.v.y; c[12 * 32] = s.v.z;
-        c[13 * 32] = F.t.x; c[14 * 32] = F.t.y; c[15 * 32] = F.t.z;
-        c[16 * 32] = F.f.x; c[17 * 32] = F.f.y; c[18 * 32] = F.f.z;
-        c[19 * 32] = __uint_as_float(rec.cnt);
-        c[20 * 32] = __uint_as_float((unsigned)rec.lo); c[21 * 32] = __uint_as_float((unsigned)(rec.lo >> 32));
-        c[22 * 32] = __uint_as_float((unsigned)rec.hi); c[23 * 32] = __uint_as_float((unsigned)(rec.hi >> 32));
-        c[24 * 32] = ang[0]; c[25 * 32] = ang[1]; c[26 * 32] = ang[2];
-        c[27 * 32] = 0.f;  // pad: the adjoint copies whole rows
-        }
-        {
-            float inv_m, I[9], inv_I[9];
-            par_load<NT>(par, inv_m, I, inv_I);
-            s = integrate_fwd(s, Rb, xc, com, F, inv_m, I, inv_I, g, A.dt);
-        }
+        float4* c = ck;
+        if (keep) { ck += ck_step; row_store_pre<RQ>(c, s, ang, rec); }
+        float inv_m, I[9], inv_I[9];
+        par_load<NT>(par, inv_m, I, inv_I);
+        const IntegratePre<float> pre = integrate_pre(s, Rb, I);
+        // ---- total wrench
+        forces_post(comm, L, Wp, Fg, (frame && A.out_jaf) ? A.out_jaf + frow * 6 : nullptr, F);
+        if (keep) row_store_post<RQ>(c, rec, F);
+        s = integrate_post(s, Rb, xc, com, F, inv_m, inv_I, g, A.dt, pre);
     }
 }
 
@@ -965,8 +1114,10 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     float4* par = (float4*)(smem + SL::par) + threadIdx.x;
     float4* xpq = (float4*)(smem + SL::xpq) + threadIdx.x;
     float4* acc = (float4*)(smem + SL::acc) + threadIdx.x;
-    volatile float* roww = smem + SL::row + (threadIdx.x >> 5) * PPR_CKPT_FLOATS * 32;  // this warp's row buffer
-    volatile float* row = roww + (threadIdx.x & 31);
+    constexpr int RQ = RowOf<JM>::kQuads;
+    constexpr int ROWF = RQ * 4 * 32;    // floats per checkpoint row of a warp
+    volatile float* roww = smem + SL::row + (threadIdx.x >> 5) * ROWF;  // this warp's row buffer
+    const float4* row4 = (const float4*)(smem + SL::row + (threadIdx.x >> 5) * ROWF) + lane;   // this lane's quads
     if (group >= A.ngroups) return;
     comm.init();
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
@@ -997,13 +1148,22 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
 
     float a_inv_m = 0.f, a_ke[3] = {0, 0, 0}, a_kd[3] = {0, 0, 0};
 
-    const float* ckw = A.ckpt + (warp * PPR_CKPT_FLOATS) * 32;  // this warp's rows (3.5 kB each, 16-byte aligned)
-    const int64_t ck_step = A.nwarps * PPR_CKPT_FLOATS * 32;
+    const float* ckw = A.ckpt + warp * ROWF;  // this warp's rows (3 / 3.5 kB each, 16-byte aligned)
+    const int64_t ck_step = A.nwarps * ROWF;
     const int64_t last = A.nsteps - 1;
     const int64_t K = RECOMP ? A.ckpt_every : 1;
     // scratch rows of this warp (RECOMP): behind the ceil(nsteps / K) stored rows of all warps
-    float* scr = A.ckpt + ((A.nsteps + K - 1) / K) * ck_step + warp * K * PPR_CKPT_FLOATS * 32;
+    float* scr = A.ckpt + ((A.nsteps + K - 1) / K) * ck_step + warp * K * ROWF;
     bool prefetched = false;
+    // -DPPR_TMA_ROWS: fetch the rows with the bulk-copy engine.  Measured on B200 (profiles/README.md, round 2): 2.5 %
+    // SLOWER than per-lane cp.async for these 3 kB per-warp rows (one more warp rendezvous + mbarrier polling per
+    // substep, and no load instruction saved that mattered), so the default stays cp.async.
+#ifdef PPR_TMA_ROWS
+    constexpr bool BULK = !RECOMP;
+#else
+    constexpr bool BULK = false;
+#endif
+    RowStream<RQ, BULK> rows(roww, (unsigned long long*)(smem + SL::rowbar) + (threadIdx.x >> 5), lane);
 
     BodyF adjN = body_zero<float>();
     // rows of the never-differentiated last substep (dp_model.py:397): zero gradient
@@ -1039,74 +1199,49 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         const int64_t seg_lo = (tp / K) * K;   // first substep of the segment tp belongs to (K = 1: tp itself)
         if (RECOMP && (tp == last - 1 || tp % K == K - 1)) {
             // ---- re-run substeps seg_lo .. tp from the stored state and park their rows in the scratch area
-            const float* c0 = ckw + (seg_lo / K) * ck_step + lane;
+            // the stored state goes through the row buffer (nothing is in flight there: prefetched == false here)
+            rows.issue(ckw + (seg_lo / K) * ck_step);
+            rows.wait();
             BodyF sr;
-            sr.x = v3<float>(c0[0 * 32], c0[1 * 32], c0[2 * 32]);
-            sr.r = q4<float>(c0[3 * 32], c0[4 * 32], c0[5 * 32], c0[6 * 32]);
-            sr.w = v3<float>(c0[7 * 32], c0[8 * 32], c0[9 * 32]);
-            sr.v = v3<float>(c0[10 * 32], c0[11 * 32], c0[12 * 32]);
+            {
+                WrenchF Fd; ContactRec rd; float ad[3];
+                row_load<RQ>(row4, sr, Fd, rd, ad);
+            }
             for (int64_t tr = seg_lo; tr <= tp; ++tr) {
                 const F3 comr = st_vec3(st, ST_COM, L.body);
                 const M3F Rr = qmat(sr.r);
                 F3 xcr = sr.x + mrot(Rr, comr);
                 load_ctl(M, L, A, tr, ke, kd, ctl);
-                WrenchF Fr;
+                WrenchF Fr, Fgr;
                 ContactRec recr;
                 float angr[3];
-                warp_forces<JM, LIMITS, QOFF>(comm, M, L, lane, sr, Rr, xcr, ctl, cm0, st, xpq, clist,
+                const WrenchF Wpr = forces_pre<JM, LIMITS, QOFF>(comm, M, L, lane, sr, Rr, xcr, ctl, cm0, st, xpq, clist,
                                               A.res_f ? A.res_f + ((tr * A.bs + L.env) * M.nb + L.body) * 6 : nullptr,
-                                              nullptr, nullptr, Fr, recr, angr);
-                float* c = scr + (tr - seg_lo) * PPR_CKPT_FLOATS * 32 + lane;
-                c[0 * 32] = sr.x.x; c[1 * 32] = sr.x.y; c[2 * 32] = sr.x.z;
-                c[3 * 32] = sr.r.x; c[4 * 32] = sr.r.y; c[5 * 32] = sr.r.z; c[6 * 32] = sr.r.w;
-                c[7 * 32] = sr.w.x; c[8 * 32] = sr.w.y; c[9 * 32] = sr.w.z;
-                c[10 * 32] = sr.v.x; c[11 * 32] = sr.v.y; c[12 * 32] = sr.v.z;
-                c[13 * 32] = Fr.t.x; c[14 * 32] = Fr.t.y; c[15 * 32] = Fr.t.z;
-                c[16 * 32] = Fr.f.x; c[17 * 32] = Fr.f.y; c[18 * 32] = Fr.f.z;
-                c[19 * 32] = __uint_as_float(recr.cnt);
-                c[20 * 32] = __uint_as_float((unsigned)recr.lo); c[21 * 32] = __uint_as_float((unsigned)(recr.lo >> 32));
-                c[22 * 32] = __uint_as_float((unsigned)recr.hi); c[23 * 32] = __uint_as_float((unsigned)(recr.hi >> 32));
-                c[24 * 32] = angr[0]; c[25 * 32] = angr[1]; c[26 * 32] = angr[2];
-                c[27 * 32] = 0.f;
+                                              nullptr, Fr, Fgr, recr, angr);
+                float4* c = (float4*)(scr + (tr - seg_lo) * ROWF) + lane;
+                row_store_pre<RQ>(c, sr, angr, recr);
+                forces_post(comm, L, Wpr, Fgr, nullptr, Fr);
+                row_store_post<RQ>(c, recr, Fr);
                 if (tr < tp) {
                     float inv_m, I[9], inv_I[9];
                     par_load<NT>(par, inv_m, I, inv_I);
                     sr = integrate_fwd(sr, Rr, xcr, comr, Fr, inv_m, I, inv_I, g, A.dt);
                 }
             }
-            __threadfence_block();
-            __syncwarp();   // the rows are read back (by other lanes) through cp.async
+            __threadfence_block();   // the rows are read back by the same lanes through cp.async
             prefetched = false;
         }
-        const float* rowsrc = RECOMP ? scr + (tp - seg_lo) * PPR_CKPT_FLOATS * 32 : ckw + tp * ck_step;
-        if (!prefetched) {   // first row (of the segment): nothing was prefetched yet
-            cp_async_row(roww, rowsrc, lane);
-            cp_async_commit();
-        }
-        cp_async_wait_all();
-        __syncwarp();        // a lane's 19+5 values were fetched by other lanes
+        const float* rowsrc = RECOMP ? scr + (tp - seg_lo) * ROWF : ckw + tp * ck_step;
+        if (!prefetched) rows.issue(rowsrc);   // first row (of the segment): nothing was prefetched yet
+        rows.wait();
         BodyF s;
         WrenchF F;
-        s.x = v3<float>(row[0 * 32], row[1 * 32], row[2 * 32]);
-        s.r = q4<float>(row[3 * 32], row[4 * 32], row[5 * 32], row[6 * 32]);
-        s.w = v3<float>(row[7 * 32], row[8 * 32], row[9 * 32]);
-        s.v = v3<float>(row[10 * 32], row[11 * 32], row[12 * 32]);
-        F.t = v3<float>(row[13 * 32], row[14 * 32], row[15 * 32]);
-        F.f = v3<float>(row[16 * 32], row[17 * 32], row[18 * 32]);
         ContactRec rec;
-        rec.cnt = __float_as_uint(row[19 * 32]);
-        rec.lo = (unsigned long long)__float_as_uint(row[20 * 32]) | ((unsigned long long)__float_as_uint(row[21 * 32]) << 32);
-        rec.hi = (unsigned long long)__float_as_uint(row[22 * 32]) | ((unsigned long long)__float_as_uint(row[23 * 32]) << 32);
         float ang[3];
-        ang[0] = row[24 * 32];
-        ang[1] = JM != JM_REVOLUTE ? row[25 * 32] : 0.f;
-        ang[2] = JM != JM_REVOLUTE ? row[26 * 32] : 0.f;
-        __syncwarp();        // everyone has read the row: refill it with the next (earlier) one of the segment
+        row_load<RQ>(row4, s, F, rec, ang);
+        // refill the buffer with the next (earlier) row of the segment
         prefetched = RECOMP ? (tp > seg_lo) : (tp > 0);
-        if (prefetched) {
-            cp_async_row(roww, RECOMP ? rowsrc - PPR_CKPT_FLOATS * 32 : ckw + (tp - 1) * ck_step, lane);
-            cp_async_commit();
-        }
+        if (prefetched) rows.issue(RECOMP ? rowsrc - ROWF : ckw + (tp - 1) * ck_step);
         const F3 com = st_vec3(st, ST_COM, L.body);
         const M3F Rb = qmat(s.r);
         M3F G = m3_zero<float>();   // dL/dRb, converted to the quaternion adjoint once at the end of the substep
@@ -1132,8 +1267,10 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
             acc[0 * NT] = q0; acc[1 * NT] = q1; acc[2 * NT] = q2; acc[3 * NT] = q3; acc[4 * NT] = q4;
         }
         comm.post_state_w(s, xc, adjF);   // published before the contact replay, awaited after it
+#ifdef PPR_CONTACTS_EARLY
         // K3^T (needs only this body's adjF)
         warp_contacts_adj(M, L, lane, s, Rb, xc, cm0, st, clist, rec, adjF, adjS, G, adj_xc);
+#endif
         // K2^T
         if (A.adj_res_f && L.valid) {
             float* r = A.adj_res_f + ((tp * A.bs + L.env) * M.nb + L.body) * 6;
@@ -1168,11 +1305,16 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
                 if (A.adj_torques) A.adj_torques[row + k] = 0.f;
             }
         }
-        comm.gather_body(adjP, L.child, L.maxc_w, adjS);
-        // world COM -> pose
+#ifndef PPR_CONTACTS_EARLY
+        // K3^T (needs only this body's adjF and feeds only this body's adjoint): after the parent adjoint is published,
+        // so that the parent is not held up by the replay of this body's contact points
+        warp_contacts_adj(M, L, lane, s, Rb, xc, cm0, st, clist, rec, adjF, adjS, G, adj_xc);
+#endif
+        // world COM -> pose: own-body part of the pose adjoint, evaluated while the children publish theirs
         adjS.x += adj_xc;
         m3_acc(G, adj_xc, com);
         adjS.r += qmat_adj(s.r, G);
+        comm.gather_body(adjP, L.child, L.maxc_w, adjS);
         adjN = adjS;
     }
     // K1^T: state 0 = eval_fk(q_init, qd_init), recomputed
@@ -1262,6 +1404,33 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
         if (c1 > c0) { for (int i = 0; i < 3; ++i) { aabb[8 * b + i] = lo[i]; aabb[8 * b + 3 + i] = hi[i]; } aabb[8 * b + 6] = dmax; }
     }
     for (int k = 0; k < D->nc; ++k) if (D->contact_body[k] < 0 || D->contact_body[k] >= nb) return PPR_E_ARG;
+    // support-function tables of the big bodies (support_lower_bound): m(n) = min_k n . p_k at the nodes of a cube map,
+    // n = (+-1, u, v) / (u, +-1, v) / (u, v, +-1) with u, v = -1 + 2 i / N; evaluated in double, rounded DOWN to float
+    std::vector<float> sup;
+    std::vector<int> sup_of(nb, -1);
+    const int big_threshold = 16;
+    for (int b = 0; b < nb; ++b) {
+        const int c0 = jinfo2[b].z, c1 = jinfo2[b].w;
+        if (c1 - c0 <= big_threshold) continue;
+        sup_of[b] = (int)(sup.size() / PPR_SUP_FLOATS);
+        for (int face = 0; face < 6; ++face)
+            for (int iv = 0; iv <= PPR_SUP_N; ++iv)
+                for (int iu = 0; iu <= PPR_SUP_N; ++iu) {
+                    const double u = -1.0 + 2.0 * iu / PPR_SUP_N, v = -1.0 + 2.0 * iv / PPR_SUP_N, sg = (face & 1) ? -1.0 : 1.0;
+                    double n[3];
+                    if (face < 2) { n[0] = sg; n[1] = u; n[2] = v; }
+                    else if (face < 4) { n[0] = u; n[1] = sg; n[2] = v; }
+                    else { n[0] = u; n[1] = v; n[2] = sg; }
+                    double best = 1e300;
+                    for (int k = c0; k < c1; ++k) {
+                        const double dd = n[0] * cpt[k].x + n[1] * cpt[k].y + n[2] * cpt[k].z;
+                        best = dd < best ? dd : best;
+                    }
+                    float f = (float)best;
+                    if ((double)f > best) f = nextafterf(f, -INFINITY);
+                    sup.push_back(f);
+                }
+    }
     std::vector<float4> lim(D->nqd > 0 ? D->nqd : 1);
     for (int k = 0; k < D->nqd; ++k)
         lim[k] = make_float4(D->joint_limit_lower[k], D->joint_limit_upper[k], D->joint_limit_ke[k], D->joint_limit_kd[k]);
@@ -1289,6 +1458,7 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
     size_t o_cpt = add(cpt.data(), cpt.size() * sizeof(float4)), o_cmat = add(cmat.data(), cmat.size() * sizeof(int));
     size_t o_mats = add(D->shape_materials, (size_t)D->nshape * 4 * sizeof(float));
     size_t o_aabb = add(aabb.data(), aabb.size() * sizeof(float));
+    size_t o_sup = add(sup.data(), sup.size() * sizeof(float)), o_supof = add(sup_of.data(), nb * sizeof(int));
 
     ppr_model* m = new (std::nothrow) ppr_model();
     if (!m) return PPR_E_ARG;
@@ -1303,7 +1473,7 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
     char* base = (char*)m->blob;
     DevModel& d = m->d;
     d.nb = nb; d.nq = D->nq; d.nqd = D->nqd; d.nc = (int)cpt.size();
-    d.epw = 32 / nb; d.maxc = maxc; d.maxdepth = maxdepth; d.big_threshold = 16;
+    d.epw = 32 / nb; d.maxc = maxc; d.maxdepth = maxdepth; d.big_threshold = big_threshold;
     d.jinfo = (const int4*)(base + o_jinfo); d.jinfo2 = (const int4*)(base + o_jinfo2);
     d.child = (const unsigned long long*)(base + o_child);
     d.order = (const int*)(base + o_order); d.pos = (const int*)(base + o_pos);
@@ -1312,6 +1482,7 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
     d.axis = (const float*)(base + o_axis); d.com = (const float*)(base + o_com);
     d.lim = (const float4*)(base + o_lim); d.cpt = (const float4*)(base + o_cpt); d.cmat = (const int*)(base + o_cmat);
     d.mats = (const float4*)(base + o_mats); d.aabb = (const float*)(base + o_aabb);
+    d.sup = (const float*)(base + o_sup); d.sup_of = (const int*)(base + o_supof);
     d.g[0] = D->gravity[0]; d.g[1] = D->gravity[1]; d.g[2] = D->gravity[2];
     d.ake = D->joint_attach_ke; d.akd = D->joint_attach_kd;
     d.mat_uniform = 1;
@@ -1366,7 +1537,11 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
             for (long long l : load) { mx = l > mx ? l : mx; sq += l * l; }
             return std::make_pair(mx, sq);
         };
-        if (any_big && !getenv("PPR_NO_BALANCE")) {
+        const char* ord = getenv("PPR_ORDER");
+        if (any_big && ord && !strcmp(ord, "cluster")) {
+            // experiment: all contact-prone bodies next to each other (one warp does the contact work of the block)
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return w[a] > w[b2]; });
+        } else if (any_big && !getenv("PPR_NO_BALANCE")) {
             auto best = cost(order);
             for (bool improved = true; improved;) {
                 improved = false;
@@ -1451,6 +1626,8 @@ extern "C" int ppr_model_group_threads(ppr_model_t m) {
 }
 
 static inline int64_t nwarps_for(const DevModel& d, int64_t n) { return (n + d.epw - 1) / d.epw; }
+// floats per body in a checkpoint row: the kernel instances of variant 0 (JM_REVOLUTE) keep 6 quads, the others 7
+static inline size_t row_floats(const ppr_model* m) { return (m->variant == 0 ? RowOf<JM_REVOLUTE>::kQuads : RowOf<JM_ALL>::kQuads) * 4; }
 // rollout kernels: groups (warps or blocks) and warps (each owns one checkpoint row per substep)
 // Small batches cannot fill 148 SMs x 4 schedulers, so what counts is the LATENCY of one substep, and that grows with
 // the number of environments a warp serialises in the contact phase: below `latency_envs` environments every
@@ -1492,6 +1669,20 @@ template <class K> static cudaError_t launch_rollout(K kernel, size_t smem, unsi
     kernel<<<grid, nt, smem, st>>>(d, A);
     return cudaGetLastError();
 }
+#ifdef PPR_AB_ONLY
+// quick A/B builds (tools/ab.sh): only the block-packed instances of the two shipped feature sets
+#define PPR_LAUNCH_ROLLOUT(KERNEL, ADJ, ...)                                                                              \
+    do {                                                                                                             \
+        cudaError_t e_ = cudaErrorInvalidValue;                                                                      \
+        DevModel d_ = m->d;                                                                                          \
+        d_.epw = epw_;                                                                                               \
+        typedef BlockComm<PPR_NT1> C_;                                                                               \
+        if (comm_ == 1 && m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, PPR_NT1, st, d_, A); \
+        else if (comm_ == 1 && m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, PPR_NT1, st, d_, A); \
+        g_launches++;                                                                                                \
+        return (int)e_;                                                                                              \
+    } while (0)
+#else
 #define PPR_LAUNCH_ROLLOUT(KERNEL, ADJ, ...)                                                                              \
     do {                                                                                                             \
         cudaError_t e_;                                                                                              \
@@ -1516,6 +1707,7 @@ template <class K> static cudaError_t launch_rollout(K kernel, size_t smem, unsi
         g_launches++;                                                                                                \
         return (int)e_;                                                                                              \
     } while (0)
+#endif
 static inline unsigned grid_for(int64_t nwarps) { return (unsigned)((nwarps * 32 + PPR_BLOCK - 1) / PPR_BLOCK); }
 
 extern "C" int ppr_fk_forward(ppr_model_t m, int64_t n, const float* q, const float* qd, float* bq, float* bqd,
@@ -1552,7 +1744,7 @@ extern "C" size_t ppr_rollout_workspace_bytes(ppr_model_t m, int64_t bs, int64_t
     rollout_geometry(m, bs, ngroups, nwarps, grid, comm_, epw_);
     const int64_t K = m->ckpt_every;
     const int64_t rows = (nsteps + K - 1) / K + (K > 1 ? K : 0);   // stored rows + per-warp scratch rows
-    return (size_t)nwarps * (size_t)rows * PPR_CKPT_FLOATS * 32 * sizeof(float);
+    return (size_t)nwarps * (size_t)rows * row_floats(m) * 32 * sizeof(float);
 }
 
 extern "C" int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t stride, float dt,
@@ -1605,7 +1797,9 @@ extern "C" int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, i
     A.adj_torques = adj_torques; A.adj_res_f = adj_res_f; A.adj_refs = adj_refs; A.adj_ke = adj_ke; A.adj_kd = adj_kd;
     A.adj_inv_m = adj_inv_m; A.adj_I = adj_I; A.adj_inv_I = adj_inv_I;
     cudaStream_t st = (cudaStream_t)stream;
+#ifndef PPR_AB_ONLY
     if (m->ckpt_every > 1) PPR_LAUNCH_ROLLOUT(rollout_backward_kernel, true, , true);
+#endif
     PPR_LAUNCH_ROLLOUT(rollout_backward_kernel, true, , false);
 }
 

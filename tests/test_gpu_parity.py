@@ -433,9 +433,10 @@ def test_c_abi_error_codes(monkeypatch):
     threads, epg = env.packing
     assert threads in (32, 96, 160) and epg == threads // env.nb
     assert env.latency_envs == 1024
-    assert lib.ppr_rollout_workspace_bytes(h, 2, 65) == 2 * 65 * 28 * 32 * 4          # latency layout: 1 env per warp
+    rowf = 24 if all(t in (1, 4) for t in env.model.joint_type) else 28    # floats per body and checkpoint row
+    assert lib.ppr_rollout_workspace_bytes(h, 2, 65) == 2 * 65 * rowf * 32 * 4        # latency layout: 1 env per warp
     env.set_latency_envs(0)
-    assert lib.ppr_rollout_workspace_bytes(h, 2, 65) == -(-2 // epg) * (threads // 32) * 65 * 28 * 32 * 4
+    assert lib.ppr_rollout_workspace_bytes(h, 2, 65) == -(-2 // epg) * (threads // 32) * 65 * rowf * 32 * 4
     assert lib.ppr_model_set_latency_envs(h, -1) == -1
     before = _lib.launch_count()
     env.fk(torch.zeros(3, env.nq, device="cuda"), torch.zeros(3, env.nqd, device="cuda"))

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Histogram of ACTIVE contact points per body and substep in a bench workload, read back from the checkpoint
-records the forward kernel writes (slot 19 of each 28-float row = count).  Needs a GPU.
+records the forward kernel writes (low halfword of float 2 of quad 3 of each row = count).  Needs a GPU.
 usage: python tools/contact_stats.py [workload] [envs]"""
 import os
 import sys
@@ -36,8 +36,10 @@ def main():
     threads, epg = env.packing
     ngroups = -(-bs // epg)
     nwarps = ngroups * (threads // 32)
-    rows = ws[: (T - 1) * nwarps * 28 * 32].view(T - 1, nwarps, 28, 32)
-    cnt = rows[:, :, 19, :].contiguous().view(torch.int32).cpu().numpy()          # T-1, nwarps, 32
+    rq = 6 if all(int(t) in (1, 4) for t in rm.joint_type) else 7                 # float4 quads per body and row
+    rows = ws[: (T - 1) * nwarps * rq * 128].view(T - 1, nwarps, rq, 32, 4)
+    cnt_all = (rows[:, :, 3, :, 2].contiguous().view(torch.int32) & 0xffff).cpu().numpy()   # T-1, nwarps, 32
+    cnt = cnt_all
     cnt = cnt.reshape(T - 1, ngroups, threads)[:, :, : epg * rm.nb]
     if threads > 32:   # block layout: slot = body * epg + env_in_group
         cnt = cnt.reshape(T - 1, ngroups, rm.nb, epg).transpose(0, 1, 3, 2)
@@ -53,7 +55,7 @@ def main():
     print("bodies with contact per env-substep: %.2f; points per touching body: mean %.2f, p50 %d, p90 %d, p99 %d, max %d"
           % ((cnt > 0).sum(-1).mean(), nz.mean(), *np.percentile(nz, [50, 90, 99]).astype(int), nz.max()))
     # the serial cost of the owner loop per warp = max over the warp's lanes; flattened = ceil(sum / 32)
-    lanes = rows[:, :, 19, :].contiguous().view(torch.int32).cpu().numpy().clip(0, 9)
+    lanes = cnt_all.clip(0, 9)
     print("per warp-substep: max over lanes %.2f (serial owner loop trips), sum over lanes %.2f (flattened work items)"
           % (lanes.max(-1).mean(), lanes.sum(-1).mean()))
     print("by time: ", np.round(cnt.sum(-1).mean((1, 2))[:: max(1, (T - 1) // 16)], 1))
