@@ -70,6 +70,9 @@ int ppr_model_set_joint_X_p(ppr_model_t m, const float* joint_X_p, void* stream)
 int ppr_model_set_joint_X_p_env(ppr_model_t m, const float* dev_joint_X_p, int64_t n_env);
 int ppr_model_set_attach(ppr_model_t m, float attach_ke, float attach_kd);
 int ppr_model_set_gravity(ppr_model_t m, const float g[3]);
+/* env.ground (dp_model.py:390): 0 skips the ground-contact kernel like compute_forces does when model.ground is False
+ * (integrator_euler.py:492-510); grf then equals res_f.  Default 1. */
+int ppr_model_set_ground(ppr_model_t m, int32_t ground);
 /* Checkpoint policy of the rollout (default 1): the forward pass keeps the per-substep state every `every` substeps;
  * the adjoint re-computes the substeps in between, segment by segment (costs (every-1)/every of a forward pass,
  * shrinks the workspace `every`-fold).  The reference keeps one full Warp State + gradient mirror per substep

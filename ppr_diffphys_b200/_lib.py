@@ -15,7 +15,7 @@ _vp, _i64, _f32 = C.c_void_p, C.c_int64, C.c_float
 
 EXPORTS = [
     "ppr_version", "ppr_model_create", "ppr_model_destroy", "ppr_model_set_joint_X_p", "ppr_model_set_joint_X_p_env", "ppr_model_set_attach",
-    "ppr_model_set_gravity", "ppr_model_set_checkpoint_every", "ppr_model_set_latency_envs",
+    "ppr_model_set_gravity", "ppr_model_set_ground", "ppr_model_set_checkpoint_every", "ppr_model_set_latency_envs",
     "ppr_model_latency_envs", "ppr_model_envs_per_group", "ppr_model_group_threads", "ppr_fk_forward", "ppr_fk_backward",
     "ppr_rollout_workspace_bytes", "ppr_rollout_forward", "ppr_rollout_backward", "ppr_se3_loss_forward",
     "ppr_se3_loss_backward", "ppr_frame_compose_forward", "ppr_frame_compose_backward", "ppr_launch_count",
@@ -34,6 +34,7 @@ def _declare(lib):
     lib.ppr_model_set_joint_X_p.argtypes = [_vp, _vp, _vp]
     lib.ppr_model_set_attach.argtypes = [_vp, _f32, _f32]
     lib.ppr_model_set_gravity.argtypes = [_vp, C.POINTER(C.c_float)]
+    lib.ppr_model_set_ground.argtypes = [_vp, C.c_int32]
     lib.ppr_model_set_checkpoint_every.argtypes = [_vp, C.c_int32]
     lib.ppr_frame_compose_forward.argtypes = [_i64, _vp, _vp, _vp, _vp, _vp, _vp]
     lib.ppr_frame_compose_backward.argtypes = [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]

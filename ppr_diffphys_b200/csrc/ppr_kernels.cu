@@ -84,6 +84,7 @@ struct DevModel {
     const int* sup_of;        // [nb] table index of the body or -1
     float g[3], ake, akd;
     int mat_uniform;          // every contact uses material row cmat[0]
+    int ground;               // 0: no ground plane, eval_body_contacts is skipped (model.ground, integrator_euler.py:492)
 };
 
 struct ppr_model {
@@ -104,6 +105,18 @@ struct ppr_model {
 #endif
 static const int kCommThreads[3] = {128, PPR_NT1, 160};
 #define PPR_MAGIC 0x50505231u
+#define PPR_MAX_DEVICES 64
+// The model's arrays live on the device that was current at ppr_model_create; every entry point that launches runs on
+// that device whatever the caller's current device is (and restores it).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int want) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != want) err = cudaSetDevice(want); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 // ----------------------------------------------------------------------------------------------- lane helpers
 __device__ __forceinline__ float shf(float v, int src) { return __shfl_sync(FULL, v, src); }
@@ -586,7 +599,7 @@ __device__ __forceinline__ int contact_candidates(const DevModel& M, const LaneI
     float ylow = s.x.y + fminf(m0 * st[(ST_AABB + 0) * 32 + b], m0 * st[(ST_AABB + 3) * 32 + b]) +
                  fminf(m1 * st[(ST_AABB + 1) * 32 + b], m1 * st[(ST_AABB + 4) * 32 + b]) +
                  fminf(m2 * st[(ST_AABB + 2) * 32 + b], m2 * st[(ST_AABB + 5) * 32 + b]) - st[(ST_AABB + 6) * 32 + b];
-    bool maybe = L.valid && (L.c1 > L.c0) && !(ylow > 1e-6f);
+    bool maybe = L.valid && M.ground && (L.c1 > L.c0) && !(ylow > 1e-6f);
     bool big = (L.c1 - L.c0) > M.big_threshold;
 #ifndef PPR_NO_SUPPORT_CULL
     if (SUP && maybe && big) {   // (every big body has a table; the index is fetched here so that it costs no register)
@@ -1486,6 +1499,7 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
     d.g[0] = D->gravity[0]; d.g[1] = D->gravity[1]; d.g[2] = D->gravity[2];
     d.ake = D->joint_attach_ke; d.akd = D->joint_attach_kd;
     d.mat_uniform = 1;
+    d.ground = 1;
     for (size_t k = 1; k < cmat.size(); ++k) if (cmat[k] != cmat[0]) d.mat_uniform = 0;
     bool any_rev = false, any_cmp = false, any_other = false, limits = false, qoffs = false;
     for (int i = 0; i < nb; ++i) {
@@ -1590,6 +1604,11 @@ extern "C" int ppr_model_set_attach(ppr_model_t m, float ke, float kd) {
     m->d.ake = ke; m->d.akd = kd;
     return 0;
 }
+extern "C" int ppr_model_set_ground(ppr_model_t m, int32_t ground) {
+    if (!check(m)) return PPR_E_HANDLE;
+    m->d.ground = ground ? 1 : 0;
+    return 0;
+}
 extern "C" int ppr_model_set_gravity(ppr_model_t m, const float g[3]) {
     if (!check(m)) return PPR_E_HANDLE;
     if (!g) return PPR_E_ARG;
@@ -1652,19 +1671,30 @@ static inline void rollout_geometry(const ppr_model* m, int64_t bs, int64_t& ngr
 }
 template <class K> static cudaError_t launch_rollout(K kernel, size_t smem, unsigned grid, int nt, cudaStream_t st,
                                                      const DevModel& d, const RolloutArgs& A) {
-    // opt in to > 48 kB of dynamic shared memory once per kernel instantiation (all instantiations share this
-    // function template because they have the same signature, hence the small pointer table)
-    static std::atomic<const void*> done[64];
+    // opt in to > 48 kB of dynamic shared memory once per (device, kernel instantiation): the attribute is per device.
+    // All instantiations share this function template (same signature), hence the small pointer table; a slot is
+    // claimed with a compare-exchange, a lost race only repeats the (idempotent) attribute call.
+    static std::atomic<const void*> done[PPR_MAX_DEVICES][64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
     bool found = false;
-    for (int i = 0; i < 64 && !found; ++i) {
-        const void* p = done[i].load(std::memory_order_acquire);
-        if (p == (const void*)kernel) found = true;
-        else if (p == nullptr) {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            done[i].store((const void*)kernel, std::memory_order_release);
-            found = true;
+    if (dev >= 0 && dev < PPR_MAX_DEVICES) {
+        for (int i = 0; i < 64 && !found; ++i) {
+            const void* p = done[dev][i].load(std::memory_order_acquire);
+            if (p == (const void*)kernel) found = true;
+            else if (p == nullptr) {
+                e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                const void* expected = nullptr;
+                done[dev][i].compare_exchange_strong(expected, (const void*)kernel, std::memory_order_acq_rel);
+                found = true;
+            }
         }
+    }
+    if (!found) {   // table full or unusual device ordinal: set it every time
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
     }
     kernel<<<grid, nt, smem, st>>>(d, A);
     return cudaGetLastError();
@@ -1713,6 +1743,8 @@ static inline unsigned grid_for(int64_t nwarps) { return (unsigned)((nwarps * 32
 extern "C" int ppr_fk_forward(ppr_model_t m, int64_t n, const float* q, const float* qd, float* bq, float* bqd,
                               void* stream) {
     if (!check(m)) return PPR_E_HANDLE;
+    DeviceGuard guard_(m->device);
+    if (guard_.err != cudaSuccess) return (int)guard_.err;
     if (n < 0 || !q || !qd || !bq || !bqd) return PPR_E_ARG;
     if (n == 0) return 0;
     dim3 grid(grid_for(nwarps_for(m->d, n)));
@@ -1727,6 +1759,8 @@ extern "C" int ppr_fk_forward(ppr_model_t m, int64_t n, const float* q, const fl
 extern "C" int ppr_fk_backward(ppr_model_t m, int64_t n, const float* q, const float* qd, const float* abq,
                                const float* abqd, float* aq, float* aqd, void* stream) {
     if (!check(m)) return PPR_E_HANDLE;
+    DeviceGuard guard_(m->device);
+    if (guard_.err != cudaSuccess) return (int)guard_.err;
     if (n < 0 || !q || !qd || !abq || !abqd || !aq || !aqd) return PPR_E_ARG;
     if (n == 0) return 0;
     dim3 grid(grid_for(nwarps_for(m->d, n)));
@@ -1753,6 +1787,8 @@ extern "C" int ppr_rollout_forward(ppr_model_t m, int64_t bs, int64_t nsteps, in
                                    const float* I, const float* inv_I, float* out_pos, float* out_vel, float* out_grf,
                                    float* out_jaf, void* ws, size_t ws_bytes, void* stream) {
     if (!check(m)) return PPR_E_HANDLE;
+    DeviceGuard guard_(m->device);
+    if (guard_.err != cudaSuccess) return (int)guard_.err;
     if (bs < 0 || nsteps < 1 || stride < 1) return PPR_E_ARG;
     if (!q_init || !qd_init || !refs || !ke || !kd || !inv_m || !I || !inv_I || !out_pos || !out_vel || !ws)
         return PPR_E_ARG;
@@ -1779,6 +1815,8 @@ extern "C" int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, i
                                     float* adj_res_f, float* adj_refs, float* adj_ke, float* adj_kd, float* adj_inv_m,
                                     float* adj_I, float* adj_inv_I, const void* ws, size_t ws_bytes, void* stream) {
     if (!check(m)) return PPR_E_HANDLE;
+    DeviceGuard guard_(m->device);
+    if (guard_.err != cudaSuccess) return (int)guard_.err;
     if (bs < 0 || nsteps < 1 || stride < 1) return PPR_E_ARG;
     if (!q_init || !qd_init || !refs || !ke || !kd || !inv_m || !I || !inv_I || !adj_pos || !adj_vel || !adj_q_init ||
         !adj_qd_init || !adj_refs || !adj_ke || !adj_kd || !adj_inv_m || !adj_I || !adj_inv_I || !ws)

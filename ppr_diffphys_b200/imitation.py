@@ -341,6 +341,11 @@ class GraphedStep:
     noise), both drawn on the host exactly like the eager path, so the two paths consume the same random stream.
     The optimizer step stays eager: its skip decision needs the gradient norm on the host (as in the reference).
 
+    Limitation: the kernel arguments are baked into the captured graph BY VALUE, including the model scalars (attach
+    gains, gravity, ground flag, checkpoint policy) and the joint_X_p pointer -- ``env.set_attach / set_gravity /
+    ground / joint_X_p = other_tensor`` after the capture are NOT seen by replays (in-place updates of a per-env
+    joint_X_p tensor are).  ``env._snapshot()`` is recorded at capture time and checked on every replay.
+
         step = GraphedStep(model)           # after model.train(); model.reinit_envs(...)
         for it in range(iters):
             model.progress = it / (iters - 1)
@@ -350,6 +355,7 @@ class GraphedStep:
     def __init__(self, model, warmup=3):
         self.model = m = model
         dev = m.device
+        self._snap = m.env._snapshot()[:-1]      # (the tensor version legitimately changes under in-place updates)
         self.frame_start = torch.zeros(m.num_envs, device=dev)
         self.noise = torch.zeros(m.num_envs, m.env.nq, device=dev)
         self._h_frame_start = torch.zeros(m.num_envs).pin_memory()
@@ -371,6 +377,8 @@ class GraphedStep:
 
     def __call__(self, frame_start=None, thresh=10.0):
         m = self.model
+        if m.env._snapshot()[:-1] != self._snap:
+            raise RuntimeError("SimEnv was modified after the CUDA graph was captured; re-create the GraphedStep")
         if frame_start is None:
             self._h_frame_start.copy_(m.compute_frame_start_host())
             self.frame_start.copy_(self._h_frame_start, non_blocking=True)

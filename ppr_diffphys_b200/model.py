@@ -326,6 +326,15 @@ class RobotModel:
     joint_attach_kd: float = 0.0
     body_names: List[str] = field(default_factory=list)
 
+    def as_builder_view(self):
+        """The four lists ``phys_model.__init__`` reads from its Warp ``articulation_builder`` to initialise the
+        ``nn.Parameter``s (dp_model.py:198-222) -- here already post-processed (inertia / mass, PD vectors)."""
+        from types import SimpleNamespace
+        return SimpleNamespace(joint_target_ke=[float(x) for x in self.joint_target_ke],
+                               joint_target_kd=[float(x) for x in self.joint_target_kd],
+                               body_mass=[float(x) for x in self.body_mass],
+                               body_inertia=np.asarray(self.norm_body_inertia, dtype=np.float32).copy())
+
     @property
     def nb(self):
         return int(self.joint_type.shape[0])

@@ -86,15 +86,32 @@ class SimEnv:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.ppr_model_create(C.byref(desc), C.byref(h)), "ppr_model_create")
         self._h = h
-        self.ground = True
+        self._ground = True
+        self.checkpoint_every = 1
+        self._gravity = tuple(float(x) for x in self.model.gravity)
         self.nb, self.nq, self.nqd = self.model.nb, self.model.nq, self.model.nqd
         self.body_count_per_env = self.nb
-        self.joint_attach_ke = float(self.model.joint_attach_ke)
-        self.joint_attach_kd = float(self.model.joint_attach_kd)
+        self._attach = [float(self.model.joint_attach_ke), float(self.model.joint_attach_kd)]
         self.body_com = torch.as_tensor(self.model.body_com)
         self._joint_X_p = torch.as_tensor(self.model.joint_X_p).clone()
 
     # -- mutable model attributes -----------------------------------------------------------------
+    @property
+    def ground(self):
+        return self._ground
+
+    @ground.setter
+    def ground(self, value):
+        """``env.ground = False`` skips the ground contacts like the reference does (integrator_euler.py:492)."""
+        self._ground = bool(value)
+        _lib.check(self._lib.ppr_model_set_ground(self._h, int(self._ground)), "ppr_model_set_ground")
+
+    def _snapshot(self):
+        """Everything of the mutable model state that a rollout's forward and backward must agree on."""
+        xp = self._joint_X_p
+        return (self.checkpoint_every, self.latency_envs, self.joint_attach_ke, self.joint_attach_kd, self._gravity,
+                self._ground, xp.data_ptr() if xp.is_cuda else None, tuple(xp.shape), xp._version)
+
     @property
     def joint_X_p(self):
         return self._joint_X_p
@@ -121,12 +138,30 @@ class SimEnv:
                        "ppr_model_set_joint_X_p")
 
     def set_attach(self, ke, kd):
-        self.joint_attach_ke, self.joint_attach_kd = float(ke), float(kd)
+        self._attach = [float(ke), float(kd)]
         _lib.check(self._lib.ppr_model_set_attach(self._h, C.c_float(ke), C.c_float(kd)), "ppr_model_set_attach")
+
+    # ``env.joint_attach_ke = ...`` / ``env.joint_attach_kd = ...`` as the reference assigns them (dp_model.py:392-393)
+    @property
+    def joint_attach_ke(self):
+        return self._attach[0]
+
+    @joint_attach_ke.setter
+    def joint_attach_ke(self, v):
+        self.set_attach(float(v), self._attach[1])
+
+    @property
+    def joint_attach_kd(self):
+        return self._attach[1]
+
+    @joint_attach_kd.setter
+    def joint_attach_kd(self, v):
+        self.set_attach(self._attach[0], float(v))
 
     def set_gravity(self, g):
         arr = (C.c_float * 3)(*[float(x) for x in g])
         _lib.check(self._lib.ppr_model_set_gravity(self._h, arr), "ppr_model_set_gravity")
+        self._gravity = tuple(float(x) for x in g)
 
     def set_checkpoint_every(self, every):
         """Checkpoint policy K of the rollout: keep the state every K substeps and let the adjoint recompute the rest
@@ -219,12 +254,6 @@ class SimEnv:
         return g
 
 
-def _scrub(g):
-    """remove_nan (dp_utils.py:43-57, clip=False): NaN -> 0. The rollout adjoint kernel already applies it at every
-    gradient store (`nan0` in ppr_kernels.cu), so this is the identity for its outputs."""
-    return g
-
-
 class ForwardKinematics(torch.autograd.Function):
     """``ForwardKinematics.apply(rj_q[T,bs,7+B], rj_qd[T,bs,6+B], env) -> (body_q[bs,T,nb,7], body_qd[bs,T,nb,6],
     body_q_numpy)`` -- dp_model.py:1022-1130. One launch for all T frames (reference: T launches + T State allocs)."""
@@ -233,6 +262,8 @@ class ForwardKinematics(torch.autograd.Function):
     def forward(ctx, rj_q, rj_qd, env):
         is_cuda = rj_q.is_cuda
         T, bs, nq = rj_q.shape
+        n_tab = env.joint_X_p.shape[0] // env.nb
+        assert n_tab in (1, bs), "per-env joint_X_p has %d blocks for %d envs" % (n_tab, bs)
         q = _f32c(rj_q, env.device).reshape(T * bs, nq)
         if rj_qd is None:
             qd = torch.zeros(T * bs, nq - 1, device=env.device, dtype=torch.float32)
@@ -290,6 +321,8 @@ class ForwardWarp(torch.autograd.Function):
                  inv_m=_f32c(body_inv_mass, dev), I=_f32c(body_inertia, dev), inv_I=_f32c(body_inv_inertia, dev))
         assert a["q_init"].numel() == bs * env.nq and a["qd_init"].numel() == bs * env.nqd
         assert a["refs"].numel() == nsteps * bs * env.nqd
+        n_tab = env.joint_X_p.shape[0] // env.nb
+        assert n_tab in (1, bs), "per-env joint_X_p has %d blocks for %d envs" % (n_tab, bs)
         # Extension of the reference signature: the five parameter tensors may be given UN-replicated
         # ([nqd], [nqd], [nb], [nb,3,3], [nb,3,3]); the kernels then read one shared copy and the returned
         # gradients are summed over envs (= the backward of dp_model.py:723-725's repeat()).
@@ -306,6 +339,7 @@ class ForwardWarp(torch.autograd.Function):
                                                      a["inv_m"], a["I"], a["inv_I"], want_forces=want_forces,
                                                      shared_params=shared)
         ctx.shared = shared
+        ctx.snap = env._snapshot()
         F = pos.shape[0]
         self.grfs = [grf[i] for i in range(F)] if want_forces else []
         self.jafs = [jaf[i] for i in range(F)] if want_forces else []
@@ -322,6 +356,12 @@ class ForwardWarp(torch.autograd.Function):
     def backward(ctx, adj_body_qs, adj_body_qd):
         env, a = ctx.env, ctx.args
         bs, nsteps, stride, dt = ctx.dims
+        if env._snapshot() != ctx.snap:
+            # the adjoint re-reads the model (checkpoint layout, attach gains, gravity, ground, joint_X_p): it must still
+            # be the one the forward pass saw, otherwise the checkpoint rows would be misread / a different model
+            # differentiated without any error
+            raise _lib.PprError("SimEnv was modified between ForwardWarp.forward and .backward "
+                                "(checkpoint policy, latency layout, attach gains, gravity, ground or joint_X_p)")
         g = env.rollout_backward(bs, nsteps, stride, dt, a["q_init"], a["qd_init"], a["torques"], a["res_f"],
                                  a["refs"], a["ke"], a["kd"], a["inv_m"], a["I"], a["inv_I"],
                                  _f32c(adj_body_qs, env.device), _f32c(adj_body_qd, env.device), ctx.ws,
@@ -331,7 +371,7 @@ class ForwardWarp(torch.autograd.Function):
         def pick(i, t, shape):
             if not need[i] or t is None:
                 return None
-            t = _scrub(t)
+            # remove_nan (dp_utils.py:43-57, clip=False) is applied by the adjoint kernel at every gradient store (nan0)
             if t.numel() != int(np.prod(shape)):  # un-replicated parameter: sum the per-env gradients
                 t = t.view(bs, -1).sum(0)
             return t.view(shape)
