@@ -123,3 +123,39 @@ def make_mixed_robot():
                       shape_materials=f32(b.shape_materials), gravity=f32([0.0, -9.80665, 0.0]),
                       joint_q_rest=f32(b.joint_q), joint_attach_ke=4000.0, joint_attach_kd=50.0,
                       body_names=list(b.body_name))
+
+
+ROLLOUT_KEYS = ["q_init", "qd_init", "torques", "res_f", "refs", "target_ke", "target_kd", "body_inv_mass",
+                "body_inertia", "body_inv_inertia"]
+
+
+def oracle_rollout_grads(rm, d, stride, F, dtype=torch.float64, adj_pos=None, adj_vel=None, loss_fn=None, dt=5e-4,
+                         keys=ROLLOUT_KEYS):
+    """oracle.sim_oracle rollout in ``dtype`` on the [bs,...] inputs ``d``; gradients of <adj_pos, pos> + <adj_vel, vel>
+    (or of ``loss_fn(pos, vel)``) w.r.t. ``keys``.  Returns pos, vel, {key: grad} as float64 CPU tensors."""
+    from oracle import sim_oracle as so
+    m = so.OracleModel(rm, dtype=dtype)
+    a = {k: d[k].to(dtype).clone().requires_grad_(k in keys) for k in ROLLOUT_KEYS}
+    pos, vel = so.rollout(m, a["q_init"], a["qd_init"], a["torques"], a["res_f"], a["refs"], a["target_ke"], a["target_kd"],
+                          a["body_inv_mass"], a["body_inertia"], a["body_inv_inertia"], dt, stride, F)[:2]
+    if loss_fn is not None:
+        loss = loss_fn(pos, vel)
+    else:
+        loss = (pos * adj_pos.to(dtype).reshape(pos.shape)).sum() + (vel * adj_vel.to(dtype).reshape(vel.shape)).sum()
+    grads = torch.autograd.grad(loss, [a[k] for k in keys], allow_unused=True)
+    out = {k: (torch.zeros_like(a[k]) if g is None else g).detach().double() for k, g in zip(keys, grads)}
+    return pos.detach().double(), vel.detach().double(), out
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def fp32_noise_floor(rm, d, stride, F, **kw):
+    """Per-key relative difference between an independent float32 evaluation (the autograd oracle run in float32) and
+    the float64 oracle on the same inputs: what single precision can resolve for this problem, whatever the code.
+    Returns ({key: floor}, float64 grads)."""
+    _, _, g64 = oracle_rollout_grads(rm, d, stride, F, dtype=torch.float64, **kw)
+    _, _, g32 = oracle_rollout_grads(rm, d, stride, F, dtype=torch.float32, **kw)
+    return {k: rel_err(g32[k], g64[k]) for k in g64}, g64

@@ -31,9 +31,12 @@ def test_cpu_port_f64_matches_golden(fixture):
         assert (g[k] - ref).norm() <= 1e-8 * ref.norm() + 1e-12, k
 
 
-@pytest.mark.parametrize("fixture", ["laikago_air", "human", "quad"])
+@pytest.mark.parametrize("fixture", ["laikago", "laikago_air", "human", "quad"])
 def test_cpu_port_f32_within_north_star_tolerance(fixture):
-    """fp32 arithmetic of the shared header vs the float64 oracle: pose <= 1e-4, gradients <= 1e-3."""
+    """fp32 arithmetic of the shared header vs the float64 oracle: pose <= 1e-4, gradients <= 1e-3 -- except laikago in
+    stiff contact, where the bound per gradient is max(1e-3, 2 x the measured fp32 noise floor) (helpers.fp32_noise_floor:
+    the autograd oracle itself re-run in float32, an evaluation that shares no code with the port)."""
+    from helpers import fp32_noise_floor
     z = np.load(os.path.join(GOLDEN, "rollout_%s.npz" % fixture))
     rm = load_robot(str(z["robot"]))
     d = {k: torch.from_numpy(z["in_" + k]).float() for k in KEYS}
@@ -41,9 +44,19 @@ def test_cpu_port_f32_within_north_star_tolerance(fixture):
     pos, vel = cpu.forward(d, float(z["dt"]), int(z["stride"]), int(z["nframes"]))
     assert (pos.double() - torch.from_numpy(z["pos"])).abs().max() < 1e-4
     g = cpu.backward(torch.from_numpy(z["adj_pos"]).float(), torch.from_numpy(z["adj_vel"]).float())
+    tol = {k: 1e-3 for k in KEYS}
+    if fixture == "laikago":
+        floor, _ = fp32_noise_floor(rm, {k: torch.from_numpy(z["in_" + k]) for k in KEYS}, int(z["stride"]),
+                                    int(z["nframes"]), adj_pos=torch.from_numpy(z["adj_pos"]),
+                                    adj_vel=torch.from_numpy(z["adj_vel"]))
+        tol = {k: max(1e-3, 2.0 * floor[k]) for k in KEYS}
+    errs = {}
     for k in KEYS:
         ref = torch.from_numpy(z["grad_" + k])
-        assert (g[k].double() - ref).norm() <= 1e-3 * ref.norm(), k
+        errs[k] = float((g[k].double() - ref).norm() / ref.norm())
+    print("\n[cpu port f32, %s] " % fixture + "; ".join("%s %.1e" % (k, errs[k]) for k in KEYS))
+    for k in KEYS:
+        assert errs[k] <= tol[k], (k, errs[k], tol[k])
 
 
 def test_cpu_port_fk_adjoint_matches_autograd():

@@ -3,7 +3,10 @@ autograd Functions, against (a) the committed golden vectors of the float64 orac
 seeded inputs, (c) size-independent properties at BASELINE.json's full sizes, (d) edge cases.
 
 Tolerances (north_star): body pose after a 64-substep window <= 1e-4 (m / quaternion component ~ rad);
-every gradient within relative error 1e-3 (norm-wise)."""
+every gradient within relative error 1e-3 (norm-wise).  One documented exception, laikago in stiff contact, where
+1e-3 is below what single precision resolves: there the bound is max(1e-3, 2 x the fp32 noise floor of that
+gradient), the floor being measured, not assumed (helpers.fp32_noise_floor: the float64 oracle re-run in float32 on
+the same inputs; tests/test_oracle.py pins its range on the CPU).  Achieved errors are printed with pytest -s."""
 import ctypes as C
 import os
 
@@ -11,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import make_inputs, make_mixed_robot, settle_height
+from helpers import fp32_noise_floor, make_inputs, make_mixed_robot, settle_height
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -20,10 +23,16 @@ KEYS = ["q_init", "qd_init", "torques", "res_f", "refs", "target_ke", "target_kd
 POS_TOL, GRAD_RTOL = 1e-4, 1e-3
 # laikago IN CONTACT is ill-conditioned in fp32: 0.16 kg lower legs on up to 96 penalty contacts of 1e4 N/m each sit
 # near the stability limit of semi-implicit Euler at dt = 5e-4 (k dt^2 / m ~ 1), so rounding differences are
-# amplified ~1e3x over a 64-substep window (the float32 CPU port differs from the float64 oracle by up to 2e-2 on
-# the same inputs while the float64 CPU port -- identical code -- matches it to 1e-11).  The airborne laikago
-# fixture and human / quad in contact hold the strict 1e-3.
-GRAD_RTOL_STIFF = 2e-2
+# amplified ~1e3x over a 64-substep window: an independent float32 evaluation of the reference formulation (the
+# autograd oracle in float32) differs from float64 by 1e-3 .. 5e-3 per gradient on the committed fixture.  The
+# tolerance for that robot is therefore per gradient max(GRAD_RTOL, 2 x measured floor); the airborne laikago fixture
+# and human / quad in contact hold the strict 1e-3.
+
+
+def grad_tolerances(rm, d, stride, F, **kw):
+    """{key: max(1e-3, 2 x fp32 noise floor)} for the inputs ``d`` ([bs,...] layout)."""
+    floor, _ = fp32_noise_floor(rm, d, stride, F, **kw)
+    return {k: max(GRAD_RTOL, 2.0 * v) for k, v in floor.items()}, floor
 
 
 @pytest.fixture(autouse=True, params=["throughput-layout", "latency-layout"])
@@ -83,10 +92,13 @@ def test_golden_forward_and_gradients(fixture):
     from ppr_diffphys_b200 import SimEnv
     z = np.load(os.path.join(GOLDEN, "rollout_%s.npz" % fixture))
     robot = str(z["robot"])
-    gtol = GRAD_RTOL_STIFF if fixture == "laikago" else GRAD_RTOL
     dev = torch.device("cuda:0")
     env = SimEnv(robot)
     d = {k: torch.from_numpy(z["in_" + k]) for k in KEYS}
+    gtol, floor = {k: GRAD_RTOL for k in KEYS}, {k: 0.0 for k in KEYS}
+    if fixture == "laikago":
+        gtol, floor = grad_tolerances(env.model, d, int(z["stride"]), int(z["nframes"]),
+                                      adj_pos=torch.from_numpy(z["adj_pos"]), adj_vel=torch.from_numpy(z["adj_vel"]))
     a, bs, T = flat_args(d, dev)
     stride, F = int(z["stride"]), int(z["nframes"])
     pos, vel, caller = run_cuda(env, a, bs, T, stride)
@@ -100,11 +112,14 @@ def test_golden_forward_and_gradients(fixture):
     adj_pos = torch.from_numpy(z["adj_pos"]).reshape(F, -1, 7).to(dev, torch.float32)
     adj_vel = torch.from_numpy(z["adj_vel"]).reshape(F, -1, 6).to(dev, torch.float32)
     torch.autograd.backward([pos, vel], [adj_pos, adj_vel])
+    errs = {}
     for k in KEYS:
         g = a[k].grad
         assert g is not None and torch.isfinite(g).all(), k
-        r = rel(g, torch.from_numpy(z["grad_" + k]))
-        assert r <= gtol, (k, r)
+        errs[k] = rel(g, torch.from_numpy(z["grad_" + k]))
+    print("\n[golden %s] " % fixture + "; ".join("%s %.1e (floor %.1e)" % (k, errs[k], floor[k]) for k in KEYS))
+    for k in KEYS:
+        assert errs[k] <= gtol[k], (k, errs[k], gtol[k])
 
 
 @pytest.mark.parametrize("robot,bs", [("laikago", 5), ("human", 2), ("quad", 3)])
@@ -133,8 +148,12 @@ def test_live_oracle_parity_null_forces(robot, bs):
     loss_c.backward()
     keys = [k for k in KEYS if k not in ("torques", "res_f")]
     grads = torch.autograd.grad(loss_o, [o[k] for k in keys])
+    tol = {k: GRAD_RTOL for k in keys}
+    if robot == "laikago":
+        d0 = dict(d, torques=d["torques"] * 0, res_f=d["res_f"] * 0)
+        tol, _ = grad_tolerances(rm, d0, stride, F, loss_fn=lambda p, v: (p ** 2).sum() + 0.1 * (v ** 2).sum(), keys=keys)
     for k, g in zip(keys, grads):
-        assert rel(a[k].grad, g) <= (GRAD_RTOL_STIFF if robot == "laikago" else GRAD_RTOL), k
+        assert rel(a[k].grad, g) <= tol[k], (k, rel(a[k].grad, g), tol[k])
 
 
 def test_generic_kernel_instance_mixed_features():
@@ -506,9 +525,11 @@ def test_per_env_joint_X_p_parity(robot):
     torch.autograd.backward([pos, vel], [wp.reshape(F, -1, 7).to(dev, torch.float32),
                                          wv.reshape(F, -1, 6).to(dev, torch.float32)])
     grads = torch.autograd.grad((opos * wp).sum() + (ovel * wv).sum(), [o[k] for k in KEYS])
-    tol = GRAD_RTOL_STIFF if robot == "laikago" else GRAD_RTOL
+    tol = {k: GRAD_RTOL for k in KEYS}
+    if robot == "laikago":
+        tol, _ = grad_tolerances(rm, d, stride, F, adj_pos=wp, adj_vel=wv)   # (shared joint_X_p: same conditioning)
     for k, gr in zip(KEYS, grads):
-        assert rel(a[k].grad, gr) <= tol, (k, rel(a[k].grad, gr))
+        assert rel(a[k].grad, gr) <= tol[k], (k, rel(a[k].grad, gr), tol[k])
     # back to one shared table: same result as a fresh model
     env.joint_X_p = torch.as_tensor(rm.joint_X_p)
     a2, _, _ = flat_args(d, dev, requires_grad=False)

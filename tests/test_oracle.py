@@ -167,3 +167,24 @@ def test_oracle_reproduces_committed_golden_vectors(fixture):
     for k, g in zip(keys, grads):
         ref = torch.from_numpy(z["grad_" + k])
         assert (g - ref).norm() <= 1e-10 * ref.norm() + 1e-14, k
+
+
+def test_fp32_noise_floor_of_the_reference_formulation():
+    """What single precision resolves on the committed fixtures, measured with the oracle itself (float32 vs float64 run
+    of the same autograd restatement): the GPU parity tests bound the CUDA gradients of laikago-in-contact by
+    max(1e-3, 2 x this floor) instead of a flat loose tolerance.  Pinned here so that a change of the oracle that moved
+    the floor (and with it the GPU tolerance) is seen on the CPU."""
+    import os
+
+    import numpy as np
+    from helpers import ROLLOUT_KEYS, fp32_noise_floor
+    from ppr_diffphys_b200 import load_robot
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for fixture, lo, hi in (("laikago", 3e-4, 1e-2), ("human", 0.0, 1e-4)):
+        z = np.load(os.path.join(golden, "rollout_%s.npz" % fixture))
+        rm = load_robot(str(z["robot"]))
+        d = {k: torch.from_numpy(z["in_" + k]) for k in ROLLOUT_KEYS}
+        floor, _ = fp32_noise_floor(rm, d, int(z["stride"]), int(z["nframes"]), adj_pos=torch.from_numpy(z["adj_pos"]),
+                                    adj_vel=torch.from_numpy(z["adj_vel"]))
+        print("\n[fp32 floor, %s] " % fixture + "; ".join("%s %.1e" % kv for kv in floor.items()))
+        assert all(lo <= v <= hi for v in floor.values()), (fixture, floor)
