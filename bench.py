@@ -168,11 +168,30 @@ class Caller:
         self.record_forces = False
 
 
+def kernel_source_hash():
+    """sha256 over the CUDA sources: profiles/traffic.json is stamped with it by tools/update_traffic.py, and a stale
+    stamp (the kernels changed since the ncu capture) is reported as such instead of being passed off as current."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "ppr_diffphys_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".h")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def workload_batch(env, w, bs, nsteps, seed, pinned_host=False):
+    """The synthetic inputs of a bench workload -- also what tests/test_gpu_bench_parity.py checks against the oracle."""
+    from ppr_diffphys_b200.synth import make_batch
+    return make_batch(env, bs, nsteps, seed=seed, clearance=w["clearance"], lin_vel=w["lin_vel"],
+                      pinned_host=pinned_host, frame_stride=w["stride"])
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
-    from ppr_diffphys_b200 import ForwardWarp, SimEnv, _lib, load_robot
-    from ppr_diffphys_b200.synth import make_batch, shared_param_chain
+    from ppr_diffphys_b200 import ForwardWarp, RefsFromFrames, SimEnv, _lib, load_robot
+    from ppr_diffphys_b200.synth import shared_param_chain
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -181,8 +200,15 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # everything runs on an ordinary (non-legacy) stream: autograd binds the gradient-accumulation nodes of the leaves
+    # to the stream of their first backward, and the legacy default stream cannot take part in a CUDA-graph capture
+    torch.cuda.set_stream(torch.cuda.Stream())
     w = WORKLOADS[args.workload]
-    bs = args.envs if args.envs else w["bs"]
+    if args.scaling == "strong":
+        total = args.total_envs if args.total_envs else w["bs"]
+        bs = total // world                       # fixed total work, sharded
+    else:
+        bs = args.envs if args.envs else w["bs"]  # fixed work per GPU
     window, stride = w["window"], w["stride"]
     nsteps = window + 1
     rm = load_robot(w["robot"])
@@ -191,43 +217,43 @@ def run_gpu_arm(args):
         env.set_checkpoint_every(args.ckpt_every)
     nb, nqd = rm.nb, rm.nqd
     caller = Caller(env, bs, nsteps, stride)
-    host = make_batch(env, bs, nsteps, seed=rank, clearance=w["clearance"], lin_vel=w["lin_vel"], pinned_host=True)
+    host = workload_batch(env, w, bs, nsteps, seed=rank, pinned_host=True)
     nI = torch.as_tensor(rm.norm_body_inertia, device=dev)
     nI_inv = torch.linalg.inv(nI)
-    # shared parameters (what the reference optimises): PD gains + body mass; per-env replication like dp_model.py:723-725
+    # shared parameters (what the reference optimises): PD gains + body mass
     p_ke = torch.as_tensor(rm.joint_target_ke, device=dev).clone().requires_grad_(True)
     p_kd = torch.as_tensor(rm.joint_target_kd, device=dev).clone().requires_grad_(True)
     p_mass = torch.as_tensor(rm.body_mass, device=dev).clone().requires_grad_(True)
-    packed = torch.zeros(2 * nqd + nb + 1, device=dev)   # shared-parameter gradients + the loss (one D2H read)
+    NP = 2 * nqd + nb + 1                         # shared-parameter gradients + the loss: one D2H read / one all-reduce
 
-    def step(inp, need_loss_host):
-        """one optimisation step of the hot path on device-resident inputs"""
+    def step(inp, replicate=False, zero_forces=False):
+        """one optimisation step of the hot path on device-resident inputs -> packed [grad ke | grad kd | grad mass | loss]"""
         q_init = inp["q_init"].detach().requires_grad_(True)
         qd_init = inp["qd_init"].detach().requires_grad_(True)
         refs = inp["refs"].detach().requires_grad_(True)
-        if args.replicate_params:   # the reference's literal calling convention: per-env replicated parameters
+        if replicate:   # the reference's literal calling convention: per-env replicated parameters (dp_model.py:723-730)
             ke, kd, mass, inv_m, I, inv_I = shared_param_chain(p_ke, p_kd, p_mass, nI, bs)
-        else:                       # un-replicated parameters: the kernels read one shared copy
+        else:           # un-replicated parameters: the kernels read one shared copy, gradients are reduced on the device
             ke, kd, mass = p_ke, p_kd, p_mass
             inv_m, I = 1.0 / p_mass, nI * p_mass[:, None, None]
             inv_I = nI_inv * inv_m[:, None, None]       # inverse(nI * m) = inverse(nI) / m
-        pos, vel = ForwardWarp.apply(q_init, qd_init, None, None, refs, ke, kd, mass, inv_m, I, inv_I, caller)
+        torques = res_f = None
+        if zero_forces:  # exact zeros passed as real tensors, as the reference does (dp_model.py:529,536)
+            torques, res_f = inp["torques0"], inp["res_f0"]
+        pos, vel = ForwardWarp.apply(q_init, qd_init, torques, res_f, refs, ke, kd, mass, inv_m, I, inv_I, caller)
         loss = (pos[-1, :, :3] - pos[0, :, :3]).pow(2).mean() + 1e-3 * vel[-1].pow(2).mean()
+        # every gradient the reference's backward returns: shared parameters (.grad of the three leaves) + per-env control
+        # references / initial state (.grad of the per-step leaves)
         for p in (p_ke, p_kd, p_mass):
             p.grad = None
         loss.backward()
-        packed[:nqd] = p_ke.grad
-        packed[nqd:2 * nqd] = p_kd.grad
-        packed[2 * nqd:2 * nqd + nb] = p_mass.grad
-        packed[-1] = loss.detach()
-        if world > 1:
-            dist.all_reduce(packed)
-        if need_loss_host:
-            return packed.cpu()       # device -> host: loss + reduced shared-parameter gradients
-        return packed
+        return torch.cat([p_ke.grad, p_kd.grad, p_mass.grad, loss.detach().reshape(1)])
 
-    dev_inp = {k: v.to(dev) for k, v in host.items()}
-    bytes_in = sum(host[k].numel() * 4 for k in ("q_init", "qd_init", "refs"))
+    keys = ("q_init", "qd_init", "refs")
+    static = {k: host[k].to(dev) for k in keys}            # inputs of the (graph-captured) step, resident in HBM
+    bytes_full = sum(host[k].numel() * 4 for k in keys)
+    ckeys = ("q_init", "qd_init", "ref_frames")
+    bytes_compact = sum(host[k].numel() * 4 for k in ckeys)
 
     def barrier():
         if world > 1:
@@ -249,16 +275,55 @@ def run_gpu_arm(args):
             ms = float(t)
         return ms
 
-    # ---- warm-up
+    # ---- warm-up (eager), then capture the step ONCE in a CUDA graph: fixed shapes, so every later step is one replay
+    # (the small / medium configs are launch-bound: 30-odd launches + autograd bookkeeping per step)
     for _ in range(max(3, args.warmup)):
-        step(dev_inp, False)
+        step(static)
+    graph, packed = None, None
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step(static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n_before = _lib.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            packed = step(static)
+        launches_per_step = _lib.launch_count() - n_before
+
+        def run_step():
+            graph.replay()
+            if world > 1:
+                dist.all_reduce(packed)
+            return packed
+    else:
+        n_before = _lib.launch_count()
+        step(static)
+        launches_per_step = _lib.launch_count() - n_before
+
+        def run_step():
+            out = step(static)
+            if world > 1:
+                dist.all_reduce(out)
+            return out
+    for _ in range(3):
+        run_step()
     # ---- device-resident timing (value)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    n0 = _lib.launch_count()
-    ms = timed(lambda: step(dev_inp, False), args.steps)
-    launches = _lib.launch_count() - n0
+    ms = timed(run_step, args.steps)
+    # the same step launched eagerly (no graph), for the host-overhead comparison
+    def eager_step():
+        out = step(static)
+        if world > 1:
+            dist.all_reduce(out)
+    for _ in range(2):   # (the first eager steps after the capture re-grow the allocator's ordinary pool)
+        eager_step()
+    ms_eager = timed(eager_step, max(3, args.steps // 4)) / max(3, args.steps // 4)
     # ---- kernel-only timing with CUDA events on the launching stream (roofline)
     ke = p_ke.detach()[None].expand(bs, nqd).reshape(-1).contiguous()
     kd = p_kd.detach()[None].expand(bs, nqd).reshape(-1).contiguous()
@@ -270,65 +335,97 @@ def run_gpu_arm(args):
     for i in range(max(args.steps, 5) + 1):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
-        pos, vel, _, _, ws = env.rollout_forward(bs, nsteps, stride, DT, dev_inp["q_init"], dev_inp["qd_init"], None,
-                                                 None, dev_inp["refs"], ke, kd, inv_m, I, inv_I, want_forces=False,
+        pos, vel, _, _, ws = env.rollout_forward(bs, nsteps, stride, DT, static["q_init"], static["qd_init"], None,
+                                                 None, static["refs"], ke, kd, inv_m, I, inv_I, want_forces=False,
                                                  workspace=ws)
         e[1].record()
-        env.rollout_backward(bs, nsteps, stride, DT, dev_inp["q_init"], dev_inp["qd_init"], None, None,
-                             dev_inp["refs"], ke, kd, inv_m, I, inv_I, pos, vel, ws)
+        env.rollout_backward(bs, nsteps, stride, DT, static["q_init"], static["qd_init"], None, None,
+                             static["refs"], ke, kd, inv_m, I, inv_I, pos, vel, ws)
         e[2].record()
         evs.append(e)
     torch.cuda.synchronize()
+    del ws, pos, vel, ke, kd, mass, inv_m, I, inv_I
     med = lambda v: sorted(v)[len(v) // 2]   # median: robust to a stray slow launch
     fwd_ms = med([e[0].elapsed_time(e[1]) for e in evs[1:]])
     bwd_ms = med([e[1].elapsed_time(e[2]) for e in evs[1:]])
-    # ---- end-to-end: host (pinned) inputs -> device, step, loss + packed shared-parameter grads -> host.
-    # Every step's inputs are copied inside the timed region; the copy of step i+1 is issued on a copy stream
-    # (double-buffered device inputs) so that it overlaps the kernels of step i.
-    keys = ("q_init", "qd_init", "refs")
+
+    # ---- end to end through the public call: what a caller SHIPS per step is q_init, qd_init and the per-FRAME control
+    # references (pinned host memory -> device, on a copy stream, double buffered so that the copy of step i+1 overlaps
+    # the kernels of step i); the per-substep references are expanded on the device (RefsFromFrames: the reference
+    # interpolates its mocap targets per substep on the host, dp_model.py:421-427,605-609); loss + packed shared
+    # gradients come back to pinned host memory every step.
     copy_stream = torch.cuda.Stream()
-    bufs = [{k: torch.empty_like(dev_inp[k]) for k in keys} for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    free = [torch.cuda.Event() for _ in range(2)]
 
-    def enqueue_copy(i):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(free[i % 2])
-            for k in keys:
-                bufs[i % 2][k].copy_(host[k], non_blocking=True)
-            ready[i % 2].record(copy_stream)
+    def make_e2e(ship_keys):
+        bufs = [{k: torch.empty_like(host[k], device=dev) for k in ship_keys} for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+        host_out = [torch.empty(NP).pin_memory() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
 
-    host_out = [torch.empty(packed.numel()).pin_memory() for _ in range(2)]
-    done = [torch.cuda.Event() for _ in range(2)]
+        def enqueue_copy(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[i % 2])
+                for k in ship_keys:
+                    bufs[i % 2][k].copy_(host[k], non_blocking=True)
+                ready[i % 2].record(copy_stream)
 
-    def e2e_run(steps):
-        """every step: H2D of its inputs (copy stream, overlapping the previous step's kernels), the step, D2H of
-        its result (loss + shared-parameter gradients) into pinned memory.  The host consumes result i after it has
-        enqueued step i+1, so the device never idles on the host round trip; the last result is awaited inside the
-        timed region."""
-        cur = torch.cuda.current_stream()
-        for b in range(2):
-            free[b].record(cur)
-        enqueue_copy(0)
-        out = None
-        for i in range(steps):
-            if i + 1 < steps:
-                enqueue_copy(i + 1)
-            cur.wait_event(ready[i % 2])
-            res = step(bufs[i % 2], False)
-            host_out[i % 2].copy_(res, non_blocking=True)   # device -> host every step
-            done[i % 2].record(cur)
-            free[i % 2].record(cur)
-            if i > 0:
-                done[(i - 1) % 2].synchronize()
-                out = float(host_out[(i - 1) % 2][-1])      # the host reads step i-1's loss
-        done[(steps - 1) % 2].synchronize()
-        out = float(host_out[(steps - 1) % 2][-1])
-        return out
+        def run(steps):
+            cur = torch.cuda.current_stream()
+            for b in range(2):
+                free[b].record(cur)
+            enqueue_copy(0)
+            out = None
+            for i in range(steps):
+                if i + 1 < steps:
+                    enqueue_copy(i + 1)
+                cur.wait_event(ready[i % 2])
+                b = bufs[i % 2]
+                static["q_init"].copy_(b["q_init"], non_blocking=True)
+                static["qd_init"].copy_(b["qd_init"], non_blocking=True)
+                if "ref_frames" in b:    # device-side expansion of the shipped per-frame references
+                    _lib.check(_lib.lib().ppr_refs_from_frames(nsteps, stride, b["ref_frames"].shape[0],
+                                                               b["ref_frames"].shape[1], b["ref_frames"].data_ptr(),
+                                                               static["refs"].data_ptr(), cur.cuda_stream),
+                               "ppr_refs_from_frames")
+                else:
+                    static["refs"].copy_(b["refs"], non_blocking=True)
+                free[i % 2].record(cur)
+                res = run_step()
+                host_out[i % 2].copy_(res, non_blocking=True)   # device -> host every step
+                done[i % 2].record(cur)
+                if i > 0:
+                    done[(i - 1) % 2].synchronize()
+                    out = float(host_out[(i - 1) % 2][-1])      # the host reads step i-1's loss
+            done[(steps - 1) % 2].synchronize()
+            return float(host_out[(steps - 1) % 2][-1])
+        return run
 
-    e2e_run(2)
-    ms_e2e = timed(lambda: e2e_run(args.steps), 1)
+    e2e_compact = make_e2e(ckeys)
+    e2e_compact(2)
+    ms_e2e = timed(lambda: e2e_compact(args.steps), 1)
+    e2e_full = make_e2e(keys)
+    e2e_full(2)
+    ms_e2e_full = timed(lambda: e2e_full(args.steps), 1)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the reference's literal calling convention: per-env replicated parameters AND exact-zero torques /
+    # res_f passed as real tensors (their gradients are computed and returned), eager
+    ref_conv = None
+    if not args.no_extras or args.reference_convention:
+        try:
+            conv = dict(static, torques0=torch.zeros(nsteps, bs * nqd, device=dev, requires_grad=True),
+                        res_f0=torch.zeros(nsteps, bs * nb, 6, device=dev, requires_grad=True))
+            for _ in range(2):
+                step(conv, replicate=True, zero_forces=True)
+            k = max(3, args.steps // 4)
+            ms_conv = timed(lambda: step(conv, replicate=True, zero_forces=True), k) / k
+            ref_conv = {"value": bs * window * world / (ms_conv * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_conv,
+                        "note": "per-env replicated ke/kd/mass/inertia + real zero torques / res_f tensors "
+                                "(dp_model.py:529,536,723-730), eager, no all-reduce"}
+            del conv
+        except Exception as ex:
+            ref_conv = {"error": repr(ex)}
 
     if rank != 0:
         if world > 1:
@@ -342,26 +439,25 @@ def run_gpu_arm(args):
     except Exception:
         pass
     peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    traffic = None
+    # DRAM traffic of the dominant kernel per launch: from the committed ncu capture IF it was taken with these sources
+    traffic, traffic_note, fp32 = None, None, None
     try:
-        if bs == w["bs"]:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload][
-                "rollout_backward_kernel"]
-    except Exception:
-        pass
-    # secondary (honest) compute bound, SURVEY.md 8(d): executed FP32 flops per env-step (2 FFMA + FADD + FMUL thread
-    # instructions, from the committed ncu capture) x measured kernel rate, against 148 SMs x 128 lanes x 2 x SM clock
-    fp32 = None
-    try:
-        fl = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]["fp32_flops_per_env_step"]
-        mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        peak_tf = 148 * 128 * 2 * mhz * 1e6 / 1e12
-        f_tf = fl["rollout_forward_kernel"] * bs * window / (fwd_ms * 1e-3) / 1e12
-        b_tf = fl["rollout_backward_kernel"] * bs * window / (bwd_ms * 1e-3) / 1e12
-        fp32 = {"flops_per_env_step": fl, "peak_tflops": peak_tf, "forward_tflops": f_tf, "backward_tflops": b_tf,
-                "forward_frac": f_tf / peak_tf, "backward_frac": b_tf / peak_tf}
-    except Exception:
-        pass
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("kernel_source_hash") != kernel_source_hash():
+            traffic_note = "profiles/traffic.json is stale (kernel sources changed since the ncu capture %s)" % tj.get(
+                "kernel_source_hash")
+        elif bs == w["bs"] and args.workload in tj:
+            traffic = tj[args.workload]["rollout_backward_kernel"]
+            fl = tj[args.workload].get("fp32_flops_per_env_step")
+            if fl:   # secondary (honest) compute bound, SURVEY.md 8(d)
+                mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                peak_tf = 148 * 128 * 2 * mhz * 1e6 / 1e12
+                f_tf = fl["rollout_forward_kernel"] * bs * window / (fwd_ms * 1e-3) / 1e12
+                b_tf = fl["rollout_backward_kernel"] * bs * window / (bwd_ms * 1e-3) / 1e12
+                fp32 = {"flops_per_env_step": fl, "peak_tflops": peak_tf, "forward_tflops": f_tf, "backward_tflops": b_tf,
+                        "forward_frac": f_tf / peak_tf, "backward_frac": b_tf / peak_tf}
+    except Exception as ex:
+        traffic_note = "profiles/traffic.json unreadable: %r" % (ex,)
     bwd_gbs = ab["bwd"] * bs * window / (bwd_ms * 1e-3) / 1e9
     fwd_gbs = ab["fwd"] * bs * window / (fwd_ms * 1e-3) / 1e9
     value = env_steps / (ms / args.steps * 1e-3)
@@ -373,19 +469,23 @@ def run_gpu_arm(args):
         except Exception as ex:  # the checker is optional for the GPU arm
             cpu = {"value": None, "unit": "env-steps/s", "cores": None, "kind": "port", "sample": "failed: %r" % (ex,)}
     others = None
-    if world == 1 and not args.no_extras and args.workload == DEFAULT_WORKLOAD and not args.envs:
-        # the remaining BASELINE.json configs (parity-test cases, not bench lines) for context: each in its own
-        # short process, device-resident step only
+    if world == 1 and not args.no_extras and args.workload == DEFAULT_WORKLOAD and not args.envs and args.scaling == "weak":
+        # the remaining BASELINE.json configs (parity-test cases, not bench lines) + the humanoid headline size, for
+        # context: each in its own short process
         others = []
-        for wname in ("laikago-trot-64x760", "quad-1024x64", "human-4096x64-contact"):
+        for wname, st in (("human-65536x64-contact", 10), ("laikago-trot-64x760", 10), ("quad-1024x64", 20),
+                          ("human-4096x64-contact", 20)):
             try:
                 out = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", wname, "--no-cpu",
-                                      "--no-extras", "--steps", "3", "--warmup", "3"], capture_output=True, text=True,
+                                      "--no-extras", "--steps", str(st), "--warmup", "3"], capture_output=True, text=True,
                                      timeout=300).stdout.strip().splitlines()[-1]
                 d = json.loads(out)
-                others.append({"workload": wname, "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
-                               "kernels_ms": d["kernels_ms"], "roofline_frac_fwd_bwd": d["roofline"]["fwd_bwd_combined_frac"],
-                               "e2e": d["e2e"]["value"]})
+                others.append({"workload": wname, "value": d["value"], "unit": d["unit"], "steps": d["steps"],
+                               "ms_per_step": d["ms_per_step"], "ms_per_step_eager": d["ms_per_step_eager"],
+                               "kernels_ms": d["kernels_ms"],
+                               "step_over_kernels": d["ms_per_step"] / (d["kernels_ms"]["rollout_forward"] + d["kernels_ms"]["rollout_backward"]),
+                               "roofline_frac_fwd_bwd": d["roofline"]["fwd_bwd_combined_frac"],
+                               "fwd_only": d["fwd_only"]["value"], "e2e": d["e2e"]["value"]})
             except Exception as ex:
                 others.append({"workload": wname, "error": repr(ex)})
         # BASELINE.json configs[0] (the reference's own recipe: laikago, mi-pace clip, 10 windows x 24 frames = 760
@@ -404,28 +504,41 @@ def run_gpu_arm(args):
     line = {
         "metric": "env_steps_per_sec_fwd_bwd", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "robot": w["robot"], "envs_per_gpu": bs, "substeps_per_window": window,
-                   "frame_stride": stride, "bodies": nb, "dofs": nqd, "contacts_per_env": rm.nc,
-                   "parallelism": "env-sharded x%d, 1 all-reduce of %d floats/step" % (world, 2 * nqd + nb + 1),
-                   "params": "per-env replicated" if args.replicate_params else "shared (un-replicated)",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "robot": w["robot"], "envs_per_gpu": bs, "total_envs": bs * world,
+                   "substeps_per_window": window, "frame_stride": stride, "bodies": nb, "dofs": nqd,
+                   "contacts_per_env": rm.nc,
+                   "refs": "per-frame samples of ja + 0.1 sin(2 pi t / 64 + phi), linear in between (mocap-style)",
+                   "parallelism": "env-sharded x%d, 1 all-reduce of %d floats/step" % (world, NP),
+                   "params": "shared (un-replicated), gradients reduced over envs in the adjoint kernel's epilogue",
+                   "step": "one CUDA-graph replay (forward kernel, loss, adjoint kernel, reduce, autograd chain)"
+                           if graph is not None else "eager launches",
+                   "math": "-prec-div=false -prec-sqrt=false -ftz=true (MUFU rcp / sqrt, <= 2 ulp; Warp's default is IEEE)",
                    "checkpoint_every": args.ckpt_every,
                    "l2": "working set >> 126 MB L2 (state checkpoint %.2f GB/step streamed once each way)"
                          % (env.workspace_bytes(bs, nsteps) / 1e9)},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches_per_step": int(launches_per_step),
+        "ms_per_step_eager": ms_eager,
         "kernels_ms": {"rollout_forward": fwd_ms, "rollout_backward": bwd_ms},
-        "fwd_only_env_steps_per_sec": bs * window / (fwd_ms * 1e-3),
+        "fwd_only": {"value": bs * window * world / (fwd_ms * 1e-3), "unit": "env-steps/s", "ms": fwd_ms,
+                     "note": "forward rollout kernel alone (CUDA events), per GPU x n_gpus"},
         "roofline": {"bound": "hbm", "kernel": "rollout_backward_kernel", "achieved": bwd_gbs, "peak": peak_gbs,
-                     "unit": "GB/s", "frac": bwd_gbs / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_env_step": ab,
+                     "unit": "GB/s", "frac": bwd_gbs / peak_gbs, "traffic": traffic, "traffic_note": traffic_note,
+                     "peak_source": peak_src, "algorithmic_bytes_per_env_step": ab,
                      "forward_kernel": {"achieved": fwd_gbs, "frac": fwd_gbs / peak_gbs},
                      "fwd_bwd_combined_frac": ab["fwdbwd"] * bs * window / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak_gbs,
+                     "step_frac": ab["fwdbwd"] * bs * window / (ms / args.steps * 1e-3) / 1e9 / peak_gbs,
                      "fp32": fp32,
-                     "note": "the path is FP32-issue / latency bound, not HBM bound (SURVEY.md 8d)"},
+                     "note": "the path is latency / issue bound, not HBM bound (SURVEY.md 8d, profiles/README.md)"},
         "e2e": {"value": env_steps / (ms_e2e / args.steps * 1e-3), "unit": "env-steps/s",
-                "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 4 * (2 * nqd + nb + 1),
-                "ms_per_step": ms_e2e / args.steps,
-                "note": "pinned-host inputs, copy of step i+1 overlapped with the kernels of step i"},
+                "h2d_bytes_per_step": bytes_compact, "d2h_bytes_per_step": 4 * NP, "ms_per_step": ms_e2e / args.steps,
+                "note": "ships q_init, qd_init and per-FRAME control references from pinned host memory (copy of step "
+                        "i+1 overlaps the kernels of step i), expands the per-substep references on the device"},
+        "e2e_full_refs_from_host": {"value": env_steps / (ms_e2e_full / args.steps * 1e-3), "unit": "env-steps/s",
+                                    "h2d_bytes_per_step": bytes_full, "ms_per_step": ms_e2e_full / args.steps,
+                                    "note": "round-1 definition: every per-substep reference shipped from the host"},
+        "reference_convention": ref_conv,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "other_configs": others,
@@ -447,8 +560,13 @@ def main():
                     help="checkpoint policy K: keep the state every K substeps, recompute the rest in the adjoint")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the other_configs context measurements")
-    ap.add_argument("--replicate-params", action="store_true",
-                    help="pass target_ke/kd, mass, inertia replicated per env like dp_model.py:723-730")
+    ap.add_argument("--reference-convention", action="store_true",
+                    help="also time the reference's literal convention (replicated parameters, real zero torques/res_f) "
+                         "even with --no-extras")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of one CUDA-graph replay")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --envs per GPU (default); strong: --total-envs sharded over the ranks")
+    ap.add_argument("--total-envs", type=int, default=0, help="total envs of a strong-scaling run (default: workload size)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

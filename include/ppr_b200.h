@@ -152,6 +152,35 @@ int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t fram
                          float* adj_body_inv_inertia, /* [bs*nb,3,3] */
                          const void* workspace, size_t workspace_bytes, void* stream);
 
+/* Shared-parameter mode with the reduction over environments done ON THE DEVICE ("backward-kernel epilogue
+ * block-reduce -> packed buffer; this replaces the repeat() backward at dp_model.py:723-725"): the five parameter inputs
+ * are the shared copies ([nqd], [nqd], [nb], [nb,3,3], [nb,3,3]) and their gradients come back already summed over the
+ * bs environments in ONE packed buffer
+ *     adj_shared = [ target_ke nqd | target_kd nqd | body_inv_mass nb | body_inertia nb*9 | body_inv_inertia nb*9 ]
+ * of ppr_rollout_shared_grad_floats(m) floats -- ready for the single all-reduce of the multi-GPU step.  The sum runs in a
+ * fixed order (per thread block in the adjoint kernel's epilogue, then over blocks): deterministic.  `scratch` is a device
+ * buffer of ppr_rollout_reduce_scratch_bytes(m, bs) bytes (one packed row per thread block). */
+int64_t ppr_rollout_shared_grad_floats(ppr_model_t m);
+size_t ppr_rollout_reduce_scratch_bytes(ppr_model_t m, int64_t bs);
+int ppr_rollout_backward_shared(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t frame_stride, float dt,
+                                const float* q_init, const float* qd_init, const float* torques, const float* res_f,
+                                const float* refs, const float* target_ke, const float* target_kd,
+                                const float* body_inv_mass, const float* body_inertia, const float* body_inv_inertia,
+                                const float* adj_out_pos, const float* adj_out_vel, float* adj_q_init, float* adj_qd_init,
+                                float* adj_torques /* or NULL */, float* adj_res_f /* or NULL */, float* adj_refs,
+                                float* adj_shared, void* scratch, size_t scratch_bytes, const void* workspace,
+                                size_t workspace_bytes, void* stream);
+
+/* ---- control references from per-frame values (part of the batch-input producer; replaces the
+ * host-side scipy interp1d of get_mocap_data for every substep, dp_model.py:421-427,605-609) -------------------------
+ * refs[t, c] = lerp(frames[t / stride, c], frames[t / stride + 1, c], (t % stride) / stride) for t < T, c < n;
+ * nframes >= (T - 1) / stride + 1 rows are read.  A caller ships nframes x n floats per window instead of T x n.
+ * backward: adj_frames [nframes, n] is OVERWRITTEN with the transpose applied to adj_refs [T, n]. */
+int ppr_refs_from_frames(int64_t T, int64_t stride, int64_t nframes, int64_t n, const float* frames, float* refs,
+                         void* stream);
+int ppr_refs_from_frames_backward(int64_t T, int64_t stride, int64_t nframes, int64_t n, const float* adj_refs,
+                                  float* adj_frames, void* stream);
+
 /* ---- se3 pose / twist loss (replaces se3_loss, dp_utils.py:113-138 with rot_angle,
  * geom_utils.py:37-46, called at dp_model.py:777,794,800) ------------------------------------------------------
  * n pairs of dim = 7 (xyz + quaternion xyzw) or dim = 6 (xyz + axis-angle) rows:

@@ -19,6 +19,8 @@ EXPORTS = [
     "ppr_model_latency_envs", "ppr_model_envs_per_group", "ppr_model_group_threads", "ppr_fk_forward", "ppr_fk_backward",
     "ppr_rollout_workspace_bytes", "ppr_rollout_forward", "ppr_rollout_backward", "ppr_se3_loss_forward",
     "ppr_se3_loss_backward", "ppr_frame_compose_forward", "ppr_frame_compose_backward", "ppr_launch_count",
+    "ppr_rollout_shared_grad_floats", "ppr_rollout_reduce_scratch_bytes", "ppr_rollout_backward_shared",
+    "ppr_refs_from_frames", "ppr_refs_from_frames_backward",
 ]
 
 
@@ -52,6 +54,13 @@ def _declare(lib):
     lib.ppr_rollout_workspace_bytes.argtypes = [_vp, _i64, _i64]
     lib.ppr_rollout_forward.argtypes = [_vp, _i64, _i64, _i64, _f32, C.c_int32] + [_vp] * 14 + [_vp, C.c_size_t, _vp]
     lib.ppr_rollout_backward.argtypes = [_vp, _i64, _i64, _i64, _f32, C.c_int32] + [_vp] * 22 + [_vp, C.c_size_t, _vp]
+    lib.ppr_rollout_shared_grad_floats.restype = _i64
+    lib.ppr_rollout_shared_grad_floats.argtypes = [_vp]
+    lib.ppr_rollout_reduce_scratch_bytes.restype = C.c_size_t
+    lib.ppr_rollout_reduce_scratch_bytes.argtypes = [_vp, _i64]
+    lib.ppr_rollout_backward_shared.argtypes = [_vp, _i64, _i64, _i64, _f32] + [_vp] * 18 + [_vp, C.c_size_t, _vp, C.c_size_t, _vp]
+    lib.ppr_refs_from_frames.argtypes = [_i64, _i64, _i64, _i64, _vp, _vp, _vp]
+    lib.ppr_refs_from_frames_backward.argtypes = [_i64, _i64, _i64, _i64, _vp, _vp, _vp]
     lib.ppr_launch_count.restype = C.c_int64
     lib.ppr_launch_count.argtypes = []
     for name in EXPORTS:

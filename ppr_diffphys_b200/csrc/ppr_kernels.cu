@@ -921,6 +921,10 @@ struct RolloutArgs {
     const float *adj_pos, *adj_vel;
     float *adj_q_init, *adj_qd_init, *adj_torques, *adj_res_f, *adj_refs, *adj_ke, *adj_kd, *adj_inv_m, *adj_I,
         *adj_inv_I;
+    // shared-parameter mode with in-kernel reduction: one row of P = 2 nqd + 19 nb floats per thread block
+    // ([ke nqd][kd nqd][inv_m nb][I nb*9][inv_I nb*9], summed over the block's environments in a fixed order);
+    // reduce_partials_kernel then sums the rows.  When set, the five per-env outputs above are not written.
+    float* adj_partial;
 };
 
 __device__ __forceinline__ void load_ctl(const DevModel& M, const LaneInfo& L, const RolloutArgs& A, int64_t t,
@@ -1013,7 +1017,8 @@ template <class Comm, bool ADJ> struct SmemLayout {
     static constexpr int clist = acc + (ADJ ? 20 * NT : 0);
     static constexpr int comm = clist + NW * 32 * PPR_CLIST_STRIDE;
     static constexpr int rowbar = comm + Comm::kExFloats + ((Comm::kExFloats & 1) ? 1 : 0);   // NW 8-byte mbarriers
-    static constexpr int total = rowbar + (ADJ ? 2 * NW : 0);
+    static constexpr int sbody = rowbar + (ADJ ? 2 * NW : 0);        // adjoint epilogue: body of every thread (-1: none)
+    static constexpr int total = sbody + (ADJ ? NT : 0);
     static constexpr size_t bytes = (size_t)total * sizeof(float);
     static_assert(comm % 4 == 0 && par % 4 == 0 && acc % 4 == 0, "float4 areas must be 16-byte aligned");
     static_assert(rowbar % 2 == 0, "mbarriers must be 8-byte aligned");
@@ -1129,6 +1134,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     float4* acc = (float4*)(smem + SL::acc) + threadIdx.x;
     constexpr int RQ = RowOf<JM>::kQuads;
     constexpr int ROWF = RQ * 4 * 32;    // floats per checkpoint row of a warp
+    ((int*)(smem + SL::sbody))[threadIdx.x] = -1;   // (threads of a partially filled last block leave right below)
     volatile float* roww = smem + SL::row + (threadIdx.x >> 5) * ROWF;  // this warp's row buffer
     const float4* row4 = (const float4*)(smem + SL::row + (threadIdx.x >> 5) * ROWF) + lane;   // this lane's quads
     if (group >= A.ngroups) return;
@@ -1339,7 +1345,41 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         BodyF s0 = warp_fk<JM>(comm, M, L2, jq, jqd);
         warp_fk_adjoint<JM>(comm, M, L2, s0, adjN, jq, jqd, A.adj_q_init, A.adj_qd_init);
     }
-    if (L.valid) {
+    if (A.adj_partial) {
+        // ---- epilogue reduction of the shared-parameter gradients over the environments of this block:
+        // every thread parks its 25 values in the (now free) joint_X_p / inertia-accumulator area, then (body, value)
+        // pairs are summed over the block's threads of that body in thread order -> deterministic
+        float* scratch = smem + SL::xpq;                 // 28 floats per thread are available, 25 used
+        float v[25];
+        v[0] = a_inv_m;
+#pragma unroll
+        for (int i = 0; i < 18; ++i) v[1 + i] = ((const float*)&acc[(i >> 2) * NT])[i & 3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { v[19 + k] = a_ke[k]; v[22 + k] = a_kd[k]; }
+        __syncthreads();                                  // everyone is done with xpq / acc
+#pragma unroll
+        for (int c = 0; c < 25; ++c) scratch[c * NT + threadIdx.x] = nan0(v[c]);
+        int* sbody = (int*)(smem + SL::sbody);
+        sbody[threadIdx.x] = L.valid ? L.body : -1;
+        __syncthreads();
+        const int P = 2 * M.nqd + 19 * M.nb;
+        float* out = A.adj_partial + (int64_t)blockIdx.x * P;
+        for (int i = threadIdx.x; i < M.nb * 25; i += NT) {
+            const int b = i / 25, c = i - b * 25;
+            float sum = 0.f;
+            for (int t = 0; t < NT; ++t) if (sbody[t] == b) sum += scratch[c * NT + t];
+            const int4 ji = M.jinfo[b];
+            const int nd = M.jinfo2[b].x;
+            if (c == 0) out[2 * M.nqd + b] = sum;
+            else if (c < 10) out[2 * M.nqd + M.nb + b * 9 + (c - 1)] = sum;
+            else if (c < 19) out[2 * M.nqd + M.nb * 10 + b * 9 + (c - 10)] = sum;
+            else {
+                const int k = (c - 19) % 3, base = (c < 22 ? 0 : M.nqd) + ji.w;
+                if (ji.x != JT_FREE) { if (k < nd) out[base + k] = sum; }
+                else { out[base + k] = 0.f; out[base + k + 3] = 0.f; }      // no PD on the six root dofs
+            }
+        }
+    } else if (L.valid) {
         A.adj_inv_m[eb] = nan0(a_inv_m);
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
@@ -1350,6 +1390,23 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) if (jon && k < L.ndof) { A.adj_ke[d + k] = nan0(a_ke[k]); A.adj_kd[d + k] = nan0(a_kd[k]); }
         if (!jon) for (int k = 0; k < L.ndof; ++k) { A.adj_ke[d + k] = 0.f; A.adj_kd[d + k] = 0.f; }
+    }
+}
+
+// rows[R][P] -> out[P], fixed summation order (deterministic): 32 columns x 8 row lanes per block
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ rows, int64_t R, int P,
+                                                              float* __restrict__ out) {
+    __shared__ float part[8][33];
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (col < P) for (int64_t r = threadIdx.y; r < R; r += 8) s += rows[r * P + col];
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < P) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+        out[col] = t;
     }
 }
 
@@ -1839,6 +1896,109 @@ extern "C" int ppr_rollout_backward(ppr_model_t m, int64_t bs, int64_t nsteps, i
     if (m->ckpt_every > 1) PPR_LAUNCH_ROLLOUT(rollout_backward_kernel, true, , true);
 #endif
     PPR_LAUNCH_ROLLOUT(rollout_backward_kernel, true, , false);
+}
+
+extern "C" int64_t ppr_rollout_shared_grad_floats(ppr_model_t m) {
+    if (!check(m)) return PPR_E_HANDLE;
+    return 2 * (int64_t)m->d.nqd + 19 * (int64_t)m->d.nb;
+}
+extern "C" size_t ppr_rollout_reduce_scratch_bytes(ppr_model_t m, int64_t bs) {
+    if (!check(m) || bs <= 0) return 0;
+    int64_t ngroups, nwarps; unsigned grid; int comm_, epw_;
+    rollout_geometry(m, bs, ngroups, nwarps, grid, comm_, epw_);
+    return (size_t)grid * (size_t)(2 * m->d.nqd + 19 * m->d.nb) * sizeof(float);
+}
+extern "C" int ppr_rollout_backward_shared(ppr_model_t m, int64_t bs, int64_t nsteps, int64_t stride, float dt,
+                                           const float* q_init, const float* qd_init, const float* torques,
+                                           const float* res_f, const float* refs, const float* ke, const float* kd,
+                                           const float* inv_m, const float* I, const float* inv_I, const float* adj_pos,
+                                           const float* adj_vel, float* adj_q_init, float* adj_qd_init, float* adj_torques,
+                                           float* adj_res_f, float* adj_refs, float* adj_shared, void* scratch,
+                                           size_t scratch_bytes, const void* ws, size_t ws_bytes, void* stream) {
+    if (!check(m)) return PPR_E_HANDLE;
+    DeviceGuard guard_(m->device);
+    if (guard_.err != cudaSuccess) return (int)guard_.err;
+    if (bs < 0 || nsteps < 1 || stride < 1) return PPR_E_ARG;
+    if (!q_init || !qd_init || !refs || !ke || !kd || !inv_m || !I || !inv_I || !adj_pos || !adj_vel || !adj_q_init ||
+        !adj_qd_init || !adj_refs || !adj_shared || !scratch || !ws)
+        return PPR_E_ARG;
+    if (bs == 0) return 0;
+    if (ws_bytes < ppr_rollout_workspace_bytes(m, bs, nsteps)) return PPR_E_WORKSPACE;
+    if (scratch_bytes < ppr_rollout_reduce_scratch_bytes(m, bs)) return PPR_E_WORKSPACE;
+    RolloutArgs A;
+    memset(&A, 0, sizeof(A));
+    unsigned grid; int comm_, epw_;
+    rollout_geometry(m, bs, A.ngroups, A.nwarps, grid, comm_, epw_);
+    A.bs = bs; A.nsteps = nsteps; A.stride = stride; A.dt = dt; A.ckpt_every = m->ckpt_every;
+    A.pstride = 0;
+    A.q_init = q_init; A.qd_init = qd_init; A.torques = torques; A.res_f = res_f; A.refs = refs; A.ke = ke; A.kd = kd;
+    A.inv_m = inv_m; A.I = I; A.inv_I = inv_I; A.ckpt = (float*)ws;
+    A.adj_pos = adj_pos; A.adj_vel = adj_vel; A.adj_q_init = adj_q_init; A.adj_qd_init = adj_qd_init;
+    A.adj_torques = adj_torques; A.adj_res_f = adj_res_f; A.adj_refs = adj_refs;
+    A.adj_partial = (float*)scratch;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = [&]() -> int {
+#ifndef PPR_AB_ONLY
+        if (m->ckpt_every > 1) PPR_LAUNCH_ROLLOUT(rollout_backward_kernel, true, , true);
+#endif
+        PPR_LAUNCH_ROLLOUT(rollout_backward_kernel, true, , false);
+    }();
+    if (rc != 0) return rc;
+    const int P = 2 * m->d.nqd + 19 * m->d.nb;
+    reduce_partials_kernel<<<(unsigned)((P + 31) / 32), dim3(32, 8), 0, st>>>((const float*)scratch, (int64_t)grid, P, adj_shared);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------- control references
+// refs[t] = lerp(key[t / stride], key[t / stride + 1], (t % stride) / stride): the per-substep control reference from
+// per-FRAME values, what get_mocap_data's interp1d does on the host for every substep of every window
+// (dp_model.py:421-427,605-609) -- a caller ships F x n floats instead of T x n.  One thread per (t, column).
+__global__ void __launch_bounds__(256)
+refs_from_frames_kernel(int64_t T, int64_t stride, int64_t nkey, int64_t n, const float* __restrict__ key,
+                        float* __restrict__ refs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * n) return;
+    const int64_t t = i / n, c = i - t * n;
+    int64_t k0 = t / stride;
+    float a = __fdiv_rn((float)(t - k0 * stride), (float)stride);
+    if (k0 >= nkey - 1) { k0 = nkey - 2 < 0 ? 0 : nkey - 2; a = nkey > 1 ? __fdiv_rn((float)(t - k0 * stride), (float)stride) : 0.f; }
+    const float v0 = key[k0 * n + c], v1 = nkey > 1 ? key[(k0 + 1) * n + c] : v0;
+    refs[i] = (1.f - a) * v0 + a * v1;    // exact at both ends of a segment
+}
+// adjoint: adj_key[k] = sum_t w(t, k) adj_refs[t]; one thread per (k, column), fixed order
+__global__ void __launch_bounds__(256)
+refs_from_frames_adj_kernel(int64_t T, int64_t stride, int64_t nkey, int64_t n, const float* __restrict__ adj_refs,
+                            float* __restrict__ adj_key) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nkey * n) return;
+    const int64_t k = i / n, c = i - k * n;
+    float s = 0.f;
+    for (int64_t t = 0; t < T; ++t) {
+        int64_t k0 = t / stride;
+        if (k0 >= nkey - 1) k0 = nkey - 2 < 0 ? 0 : nkey - 2;
+        const float a = nkey > 1 ? __fdiv_rn((float)(t - k0 * stride), (float)stride) : 0.f;
+        if (k == k0) s += (1.f - a) * adj_refs[t * n + c];
+        else if (k == k0 + 1) s += a * adj_refs[t * n + c];
+    }
+    adj_key[i] = nan0(s);
+}
+extern "C" int ppr_refs_from_frames(int64_t T, int64_t stride, int64_t nkey, int64_t n, const float* key, float* refs,
+                                    void* stream) {
+    if (T < 0 || stride < 1 || nkey < 1 || n < 0 || !key || !refs) return PPR_E_ARG;
+    if (T * n == 0) return 0;
+    refs_from_frames_kernel<<<(unsigned)((T * n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, stride, nkey, n, key, refs);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+extern "C" int ppr_refs_from_frames_backward(int64_t T, int64_t stride, int64_t nkey, int64_t n, const float* adj_refs,
+                                             float* adj_key, void* stream) {
+    if (T < 0 || stride < 1 || nkey < 1 || n < 0 || !adj_refs || !adj_key) return PPR_E_ARG;
+    if (nkey * n == 0) return 0;
+    refs_from_frames_adj_kernel<<<(unsigned)((nkey * n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, stride, nkey, n,
+                                                                                                   adj_refs, adj_key);
+    g_launches++;
+    return (int)cudaGetLastError();
 }
 
 // ----------------------------------------------------------------------------------------------- se3 loss

@@ -254,6 +254,32 @@ class SimEnv:
         return g
 
 
+    def rollout_backward_shared(self, bs, nsteps, stride, dt, q_init, qd_init, torques, res_f, refs, ke, kd, inv_m, I, inv_I,
+                                adj_pos, adj_vel, workspace):
+        """Adjoint with UN-replicated parameters; their gradients come back summed over the environments (reduced in
+        the adjoint kernel's epilogue + one small reduce kernel) as views of ONE packed buffer ``g["packed"]`` =
+        [target_ke | target_kd | body_inv_mass | body_inertia | body_inv_inertia]."""
+        dev, nb, nqd = self.device, self.nb, self.nqd
+        e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        P = 2 * nqd + 19 * nb
+        packed = e(P)
+        scratch = e((int(self._lib.ppr_rollout_reduce_scratch_bytes(self._h, bs)) + 3) // 4)
+        g = dict(q_init=e(bs * self.nq), qd_init=e(bs * nqd),
+                 torques=e(nsteps, bs * nqd) if torques is not None else None,
+                 res_f=e(nsteps, bs * nb, 6) if res_f is not None else None, refs=e(nsteps, bs * nqd), packed=packed,
+                 target_ke=packed[:nqd], target_kd=packed[nqd:2 * nqd], body_inv_mass=packed[2 * nqd:2 * nqd + nb],
+                 body_inertia=packed[2 * nqd + nb:2 * nqd + 10 * nb].view(nb, 3, 3),
+                 body_inv_inertia=packed[2 * nqd + 10 * nb:].view(nb, 3, 3))
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.ppr_rollout_backward_shared(
+                self._h, bs, nsteps, stride, C.c_float(dt), _ptr(q_init), _ptr(qd_init), _ptr(torques), _ptr(res_f),
+                _ptr(refs), _ptr(ke), _ptr(kd), _ptr(inv_m), _ptr(I), _ptr(inv_I), _ptr(adj_pos), _ptr(adj_vel),
+                _ptr(g["q_init"]), _ptr(g["qd_init"]), _ptr(g["torques"]), _ptr(g["res_f"]), _ptr(g["refs"]),
+                _ptr(packed), _ptr(scratch), C.c_size_t(scratch.numel() * 4), _ptr(workspace),
+                C.c_size_t(workspace.numel() * 4), _stream()), "ppr_rollout_backward_shared")
+        return g
+
+
 class ForwardKinematics(torch.autograd.Function):
     """``ForwardKinematics.apply(rj_q[T,bs,7+B], rj_qd[T,bs,6+B], env) -> (body_q[bs,T,nb,7], body_qd[bs,T,nb,6],
     body_q_numpy)`` -- dp_model.py:1022-1130. One launch for all T frames (reference: T launches + T State allocs)."""
@@ -362,19 +388,16 @@ class ForwardWarp(torch.autograd.Function):
             # differentiated without any error
             raise _lib.PprError("SimEnv was modified between ForwardWarp.forward and .backward "
                                 "(checkpoint policy, latency layout, attach gains, gravity, ground or joint_X_p)")
-        g = env.rollout_backward(bs, nsteps, stride, dt, a["q_init"], a["qd_init"], a["torques"], a["res_f"],
-                                 a["refs"], a["ke"], a["kd"], a["inv_m"], a["I"], a["inv_I"],
-                                 _f32c(adj_body_qs, env.device), _f32c(adj_body_qd, env.device), ctx.ws,
-                                 shared_params=ctx.shared)
+        fn = env.rollout_backward_shared if ctx.shared else env.rollout_backward
+        g = fn(bs, nsteps, stride, dt, a["q_init"], a["qd_init"], a["torques"], a["res_f"], a["refs"], a["ke"], a["kd"],
+               a["inv_m"], a["I"], a["inv_I"], _f32c(adj_body_qs, env.device), _f32c(adj_body_qd, env.device), ctx.ws)
         need, sh = ctx.needs_input_grad, ctx.shapes
 
         def pick(i, t, shape):
             if not need[i] or t is None:
                 return None
             # remove_nan (dp_utils.py:43-57, clip=False) is applied by the adjoint kernel at every gradient store (nan0)
-            if t.numel() != int(np.prod(shape)):  # un-replicated parameter: sum the per-env gradients
-                t = t.view(bs, -1).sum(0)
-            return t.view(shape)
+            return t.reshape(shape)    # (un-replicated parameters: already summed over envs on the device)
         body_mass_grad = torch.zeros(sh["mass"], device=env.device) if need[7] else None  # K5 never reads m
         return (pick(0, g["q_init"], sh["q_init"]), pick(1, g["qd_init"], sh["qd_init"]),
                 pick(2, g["torques"], sh["torques"]), pick(3, g["res_f"], sh["res_f"]),
@@ -449,3 +472,30 @@ class FrameCompose(torch.autograd.Function):
                                                              _ptr(adj_g), _ptr(adj_d), _stream()),
                        "ppr_frame_compose_backward")
         return (adj_g.sum(0) if ctx.needs_input_grad[0] else None), None, (adj_d if ctx.needs_input_grad[2] else None)
+
+
+class RefsFromFrames(torch.autograd.Function):
+    """``RefsFromFrames.apply(frames[F, n], stride, T) -> refs[T, n]``: per-substep control references linearly
+    interpolated from per-frame values on the device -- what ``get_mocap_data``'s scipy ``interp1d`` does on the host for
+    every substep of every window (dp_model.py:421-427,605-609).  A caller ships F x n floats instead of T x n."""
+
+    @staticmethod
+    def forward(ctx, frames, stride, T):
+        assert frames.is_cuda and frames.dim() == 2 and frames.shape[0] >= (T - 1) // stride + 1
+        f = _f32c(frames, frames.device)
+        refs = torch.empty(T, f.shape[1], device=f.device, dtype=torch.float32)
+        with torch.cuda.device(f.device):
+            _lib.check(_lib.lib().ppr_refs_from_frames(T, stride, f.shape[0], f.shape[1], _ptr(f), _ptr(refs), _stream()),
+                       "ppr_refs_from_frames")
+        ctx.dims = (T, stride, f.shape[0], f.shape[1])
+        return refs
+
+    @staticmethod
+    def backward(ctx, adj_refs):
+        T, stride, F, n = ctx.dims
+        a = _f32c(adj_refs, adj_refs.device)
+        adj = torch.empty(F, n, device=a.device, dtype=torch.float32)
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.lib().ppr_refs_from_frames_backward(T, stride, F, n, _ptr(a), _ptr(adj), _stream()),
+                       "ppr_refs_from_frames_backward")
+        return adj, None, None

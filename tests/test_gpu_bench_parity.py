@@ -49,7 +49,6 @@ def bench_loss(pos, vel):
 def test_bench_workload_matches_oracle(case, layout, monkeypatch):
     import bench
     from ppr_diffphys_b200 import ForwardWarp, SimEnv, load_robot
-    from ppr_diffphys_b200.synth import make_batch
     monkeypatch.setenv("PPR_LATENCY_ENVS", "0" if layout == "throughput-layout" else "1000000")
     wname, clr, lv = CASES[case]
     w = bench.WORKLOADS[wname]
@@ -61,7 +60,11 @@ def test_bench_workload_matches_oracle(case, layout, monkeypatch):
     rm = load_robot(w["robot"])
     dev = torch.device("cuda:0")
     env = SimEnv(rm)
-    host = make_batch(env, N_DRAW, nsteps, seed=0, clearance=clearance, lin_vel=lin_vel)   # bench.py:194
+    host = bench.workload_batch(env, dict(w, clearance=clearance, lin_vel=lin_vel), N_DRAW, nsteps, seed=0)
+    # (the per-substep references are the device expansion of the shipped per-frame ones: same arithmetic)
+    from ppr_diffphys_b200 import RefsFromFrames
+    dev_refs = RefsFromFrames.apply(host["ref_frames"].cuda(), stride, nsteps)
+    assert torch.equal(dev_refs.cpu(), host["refs"])
     pick = torch.linspace(0, N_DRAW - 1, N_PICK).round().long()
     nb, nq, nqd = rm.nb, rm.nq, rm.nqd
     q_init = host["q_init"].view(N_DRAW, nq)[pick].contiguous()
