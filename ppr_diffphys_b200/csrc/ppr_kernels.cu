@@ -1364,7 +1364,9 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         __syncthreads();
         const int P = 2 * M.nqd + 19 * M.nb;
         float* out = A.adj_partial + (int64_t)blockIdx.x * P;
-        for (int i = threadIdx.x; i < M.nb * 25; i += NT) {
+        // (warp layout: the warps of a partially filled last block that own no environment have left the kernel)
+        const int nalive = Comm::kBlock ? NT : (int)min((int64_t)NT, (A.ngroups - (int64_t)blockIdx.x * (NT / 32)) * 32);
+        for (int i = threadIdx.x; i < M.nb * 25; i += nalive) {
             const int b = i / 25, c = i - b * 25;
             float sum = 0.f;
             for (int t = 0; t < NT; ++t) if (sbody[t] == b) sum += scratch[c * NT + t];
