@@ -171,6 +171,37 @@ int ppr_rollout_backward_shared(ppr_model_t m, int64_t bs, int64_t nsteps, int64
                                 float* adj_shared, void* scratch, size_t scratch_bytes, const void* workspace,
                                 size_t workspace_bytes, void* stream);
 
+/* ---- struct-argument form of the rollout: every option in one place.  Zero-initialise, fill what applies. --------------
+ * Adds to the positional entry points above the FUSED POSE LOSS of the imitation objective (SURVEY.md 8f rank 1;
+ * se3_loss(sim_position, target_position), dp_model.py:777 with dp_utils.py:113-138): with `target_pos` [F, bs*nb, 7]
+ * and `loss_pos` [F, bs*nb] set, the forward kernel evaluates the per-body pose loss at the frame steps while the pose is
+ * still in registers; with `adj_loss_pos` [F, bs*nb] (= d objective / d loss_pos, from the caller's mean / clipping) the
+ * adjoint kernel seeds itself from it, `target_pos` and the frame poses in `out_pos` -- no adj_pos tensor, no separate loss
+ * kernels.  `adj_out_pos` / `adj_out_vel` stay available (either may be NULL) and are added on top. */
+typedef struct ppr_rollout_io {
+    int64_t bs, nsteps, frame_stride;
+    float dt;
+    int32_t shared_params;
+    const float *q_init, *qd_init, *torques, *res_f, *refs, *target_ke, *target_kd, *body_inv_mass, *body_inertia,
+        *body_inv_inertia;                                  /* as ppr_rollout_forward */
+    float *out_pos, *out_vel, *out_grf, *out_jaf;           /* forward outputs; out_pos is READ by backward_ex when the loss is fused */
+    void* workspace;
+    size_t workspace_bytes;
+    const float* target_pos;                                /* [F, bs*nb, 7] or NULL */
+    float rot_ratio;                                        /* weight of the rotation angle in the pose loss (reference: 0.1) */
+    float* loss_pos;                                        /* forward: [F, bs*nb] or NULL */
+    const float* adj_loss_pos;                              /* backward: [F, bs*nb] or NULL */
+    float* adj_target_pos;                                  /* backward: [F, bs*nb, 7] or NULL -- gradient w.r.t. the targets */
+    const float *adj_out_pos, *adj_out_vel;                 /* backward: [F, bs*nb, 7] / [F, bs*nb, 6], each may be NULL */
+    float *adj_q_init, *adj_qd_init, *adj_torques, *adj_res_f, *adj_refs;
+    float *adj_target_ke, *adj_target_kd, *adj_body_inv_mass, *adj_body_inertia, *adj_body_inv_inertia; /* per-env form */
+    float* adj_shared;                                      /* or: packed sums over envs (see ppr_rollout_backward_shared) */
+    void* reduce_scratch;
+    size_t reduce_scratch_bytes;
+} ppr_rollout_io;
+int ppr_rollout_forward_ex(ppr_model_t m, const ppr_rollout_io* io, void* stream);
+int ppr_rollout_backward_ex(ppr_model_t m, const ppr_rollout_io* io, void* stream);
+
 /* ---- control references from per-frame values (part of the batch-input producer; replaces the
  * host-side scipy interp1d of get_mocap_data for every substep, dp_model.py:421-427,605-609) -------------------------
  * refs[t, c] = lerp(frames[t / stride, c], frames[t / stride + 1, c], (t % stride) / stride) for t < T, c < n;

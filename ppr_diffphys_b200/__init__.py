@@ -11,8 +11,8 @@ library (``libppr_b200.so``) is missing -- there is no CPU fallback.
 from .model import RobotModel, compile_robot, load_robot, ROBOT_PRESETS  # noqa: F401
 
 __all__ = ["RobotModel", "compile_robot", "load_robot", "ROBOT_PRESETS"]
-from .ops import (ForwardKinematics, ForwardWarp, FrameCompose, RefsFromFrames, Se3Loss, SimEnv, convert_ppr_warp,  # noqa: E402,F401
+from .ops import (ForwardKinematics, ForwardWarp, ForwardWarpLoss, FrameCompose, RefsFromFrames, Se3Loss, SimEnv, convert_ppr_warp,  # noqa: E402,F401
                   LazyFrames)
 
-__all__ += ["ForwardKinematics", "ForwardWarp", "FrameCompose", "RefsFromFrames", "Se3Loss", "SimEnv", "convert_ppr_warp",
+__all__ += ["ForwardKinematics", "ForwardWarp", "ForwardWarpLoss", "FrameCompose", "RefsFromFrames", "Se3Loss", "SimEnv", "convert_ppr_warp",
             "LazyFrames"]

@@ -51,3 +51,25 @@ def make_desc(rm):
     d.gravity[0], d.gravity[1], d.gravity[2] = float(g[0]), float(g[1]), float(g[2])
     d.joint_attach_ke, d.joint_attach_kd = float(rm.joint_attach_ke), float(rm.joint_attach_kd)
     return d, keep
+
+
+_vp = C.c_void_p
+
+
+class RolloutIO(C.Structure):
+    """struct ppr_rollout_io (include/ppr_b200.h): every option of the rollout; pointers are raw device addresses."""
+    _fields_ = [
+        ("bs", C.c_int64), ("nsteps", C.c_int64), ("frame_stride", C.c_int64), ("dt", C.c_float),
+        ("shared_params", C.c_int32),
+        ("q_init", _vp), ("qd_init", _vp), ("torques", _vp), ("res_f", _vp), ("refs", _vp), ("target_ke", _vp),
+        ("target_kd", _vp), ("body_inv_mass", _vp), ("body_inertia", _vp), ("body_inv_inertia", _vp),
+        ("out_pos", _vp), ("out_vel", _vp), ("out_grf", _vp), ("out_jaf", _vp),
+        ("workspace", _vp), ("workspace_bytes", C.c_size_t),
+        ("target_pos", _vp), ("rot_ratio", C.c_float), ("loss_pos", _vp), ("adj_loss_pos", _vp),
+        ("adj_target_pos", _vp),
+        ("adj_out_pos", _vp), ("adj_out_vel", _vp),
+        ("adj_q_init", _vp), ("adj_qd_init", _vp), ("adj_torques", _vp), ("adj_res_f", _vp), ("adj_refs", _vp),
+        ("adj_target_ke", _vp), ("adj_target_kd", _vp), ("adj_body_inv_mass", _vp), ("adj_body_inertia", _vp),
+        ("adj_body_inv_inertia", _vp),
+        ("adj_shared", _vp), ("reduce_scratch", _vp), ("reduce_scratch_bytes", C.c_size_t),
+    ]

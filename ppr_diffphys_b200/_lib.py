@@ -5,7 +5,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from ._capi import ModelDesc
+from ._capi import ModelDesc, RolloutIO
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PPR_B200_LIB") or os.path.join(_HERE, "libppr_b200.so")  # env override: A/B builds
@@ -20,7 +20,7 @@ EXPORTS = [
     "ppr_rollout_workspace_bytes", "ppr_rollout_forward", "ppr_rollout_backward", "ppr_se3_loss_forward",
     "ppr_se3_loss_backward", "ppr_frame_compose_forward", "ppr_frame_compose_backward", "ppr_launch_count",
     "ppr_rollout_shared_grad_floats", "ppr_rollout_reduce_scratch_bytes", "ppr_rollout_backward_shared",
-    "ppr_refs_from_frames", "ppr_refs_from_frames_backward",
+    "ppr_refs_from_frames", "ppr_refs_from_frames_backward", "ppr_rollout_forward_ex", "ppr_rollout_backward_ex",
 ]
 
 
@@ -61,6 +61,8 @@ def _declare(lib):
     lib.ppr_rollout_backward_shared.argtypes = [_vp, _i64, _i64, _i64, _f32] + [_vp] * 18 + [_vp, C.c_size_t, _vp, C.c_size_t, _vp]
     lib.ppr_refs_from_frames.argtypes = [_i64, _i64, _i64, _i64, _vp, _vp, _vp]
     lib.ppr_refs_from_frames_backward.argtypes = [_i64, _i64, _i64, _i64, _vp, _vp, _vp]
+    lib.ppr_rollout_forward_ex.argtypes = [_vp, C.POINTER(RolloutIO), _vp]
+    lib.ppr_rollout_backward_ex.argtypes = [_vp, C.POINTER(RolloutIO), _vp]
     lib.ppr_launch_count.restype = C.c_int64
     lib.ppr_launch_count.argtypes = []
     for name in EXPORTS:

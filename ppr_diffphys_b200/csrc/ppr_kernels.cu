@@ -925,6 +925,15 @@ struct RolloutArgs {
     // ([ke nqd][kd nqd][inv_m nb][I nb*9][inv_I nb*9], summed over the block's environments in a fixed order);
     // reduce_partials_kernel then sums the rows.  When set, the five per-env outputs above are not written.
     float* adj_partial;
+    // fused pose loss at the frame steps (se3_loss of dp_utils.py:113-138 on sim vs target poses, dp_model.py:777):
+    // forward writes loss_pos[F, bs*nb]; the adjoint seeds itself from adj_loss_pos[F, bs*nb], the target poses and the
+    // frame poses the forward pass wrote (saved_pos = out_pos) -- no adj_pos tensor, no separate loss kernels
+    const float* target_pos;
+    float* loss_pos;
+    const float* adj_loss_pos;
+    const float* saved_pos;
+    float* adj_target_pos;     // optional: d objective / d target_pos [F, bs*nb, 7] (the targets depend on global_q)
+    float rot_ratio;
 };
 
 __device__ __forceinline__ void load_ctl(const DevModel& M, const LaneInfo& L, const RolloutArgs& A, int64_t t,
@@ -1083,6 +1092,12 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
             o[0] = s.x.x; o[1] = s.x.y; o[2] = s.x.z; o[3] = s.r.x; o[4] = s.r.y; o[5] = s.r.z; o[6] = s.r.w;
             float* v = A.out_vel + frow * 6;
             v[0] = s.w.x; v[1] = s.w.y; v[2] = s.w.z; v[3] = s.v.x; v[4] = s.v.y; v[5] = s.v.z;
+            if (A.loss_pos) {
+                const float* tg = A.target_pos + frow * 7;
+                const float pp[7] = {s.x.x, s.x.y, s.x.z, s.r.x, s.r.y, s.r.z, s.r.w};
+                const float gg[7] = {tg[0], tg[1], tg[2], tg[3], tg[4], tg[5], tg[6]};
+                A.loss_pos[frow] = se3_pair_loss<float>(7, pp, gg, A.rot_ratio, 1e-4f);
+            }
         }
         // the substep past the last frame exists only for the force side channels (dp_model.py:397): skip it
         // when nobody asked for them
@@ -1206,12 +1221,32 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         if (frame) { fphase = A.stride - 1; --fi; } else --fphase;
         if (frame && L.valid) {
             int64_t frow = (fcur * A.bs + L.env) * M.nb + L.body;
-            const float* a = A.adj_pos + frow * 7;
-            const float* b = A.adj_vel + frow * 6;
-            adjN.x += v3<float>(a[0], a[1], a[2]);
-            adjN.r += q4<float>(a[3], a[4], a[5], a[6]);
-            adjN.w += v3<float>(b[0], b[1], b[2]);
-            adjN.v += v3<float>(b[3], b[4], b[5]);
+            if (A.adj_pos) {
+                const float* a = A.adj_pos + frow * 7;
+                adjN.x += v3<float>(a[0], a[1], a[2]);
+                adjN.r += q4<float>(a[3], a[4], a[5], a[6]);
+            }
+            if (A.adj_vel) {
+                const float* b = A.adj_vel + frow * 6;
+                adjN.w += v3<float>(b[0], b[1], b[2]);
+                adjN.v += v3<float>(b[3], b[4], b[5]);
+            }
+            if (A.adj_loss_pos) {   // fused pose loss: d loss / d pose from the saved frame pose and the target
+                const float* sp = A.saved_pos + frow * 7;
+                const float* tg = A.target_pos + frow * 7;
+                const float pp[7] = {sp[0], sp[1], sp[2], sp[3], sp[4], sp[5], sp[6]};
+                const float gg[7] = {tg[0], tg[1], tg[2], tg[3], tg[4], tg[5], tg[6]};
+                float ap[7], ag[7];
+                se3_pair_loss_adj<float>(7, pp, gg, A.rot_ratio, 1e-4f, A.adj_loss_pos[frow], ap,
+                                         A.adj_target_pos ? ag : (float*)nullptr);
+                if (A.adj_target_pos) {
+                    float* o = A.adj_target_pos + frow * 7;
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) o[k] = nan0(ag[k]);
+                }
+                adjN.x += v3<float>(nan0(ap[0]), nan0(ap[1]), nan0(ap[2]));
+                adjN.r += q4<float>(nan0(ap[3]), nan0(ap[4]), nan0(ap[5]), nan0(ap[6]));
+            }
         }
         if (t == 0) break;
         int64_t tp = t - 1;  // differentiate substep tp -> t
@@ -1948,6 +1983,78 @@ extern "C" int ppr_rollout_backward_shared(ppr_model_t m, int64_t bs, int64_t ns
     if (rc != 0) return rc;
     const int P = 2 * m->d.nqd + 19 * m->d.nb;
     reduce_partials_kernel<<<(unsigned)((P + 31) / 32), dim3(32, 8), 0, st>>>((const float*)scratch, (int64_t)grid, P, adj_shared);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+
+// ---- struct-argument entry points: every option of the rollout in one place (shared parameters, device-side reduction
+// of their gradients, fused pose loss); the positional entry points above are the reference-shaped subset
+static int fill_args(ppr_model* m, const ppr_rollout_io* io, RolloutArgs& A, unsigned& grid, int& comm_, int& epw_) {
+    if (io->bs < 0 || io->nsteps < 1 || io->frame_stride < 1) return PPR_E_ARG;
+    if (!io->q_init || !io->qd_init || !io->refs || !io->target_ke || !io->target_kd || !io->body_inv_mass ||
+        !io->body_inertia || !io->body_inv_inertia || !io->out_pos || !io->out_vel || !io->workspace)
+        return PPR_E_ARG;
+    if ((io->loss_pos || io->adj_loss_pos) && !io->target_pos) return PPR_E_ARG;
+    memset(&A, 0, sizeof(A));
+    if (io->bs == 0) return 0;
+    if (io->workspace_bytes < ppr_rollout_workspace_bytes(m, io->bs, io->nsteps)) return PPR_E_WORKSPACE;
+    rollout_geometry(m, io->bs, A.ngroups, A.nwarps, grid, comm_, epw_);
+    A.bs = io->bs; A.nsteps = io->nsteps; A.stride = io->frame_stride; A.dt = io->dt; A.ckpt_every = m->ckpt_every;
+    A.pstride = io->shared_params ? 0 : 1;
+    A.q_init = io->q_init; A.qd_init = io->qd_init; A.torques = io->torques; A.res_f = io->res_f; A.refs = io->refs;
+    A.ke = io->target_ke; A.kd = io->target_kd; A.inv_m = io->body_inv_mass; A.I = io->body_inertia;
+    A.inv_I = io->body_inv_inertia; A.ckpt = (float*)io->workspace;
+    A.target_pos = io->target_pos; A.rot_ratio = io->rot_ratio;
+    return 0;
+}
+extern "C" int ppr_rollout_forward_ex(ppr_model_t m, const ppr_rollout_io* io, void* stream) {
+    if (!check(m)) return PPR_E_HANDLE;
+    if (!io) return PPR_E_ARG;
+    DeviceGuard guard_(m->device);
+    if (guard_.err != cudaSuccess) return (int)guard_.err;
+    RolloutArgs A;
+    unsigned grid = 0; int comm_ = 0, epw_ = 1;
+    int rc = fill_args(m, io, A, grid, comm_, epw_);
+    if (rc != 0 || io->bs == 0) return rc;
+    A.out_pos = io->out_pos; A.out_vel = io->out_vel; A.out_grf = io->out_grf; A.out_jaf = io->out_jaf;
+    A.loss_pos = io->loss_pos;
+    cudaStream_t st = (cudaStream_t)stream;
+    PPR_LAUNCH_ROLLOUT(rollout_forward_kernel, false, );
+}
+extern "C" int ppr_rollout_backward_ex(ppr_model_t m, const ppr_rollout_io* io, void* stream) {
+    if (!check(m)) return PPR_E_HANDLE;
+    if (!io) return PPR_E_ARG;
+    DeviceGuard guard_(m->device);
+    if (guard_.err != cudaSuccess) return (int)guard_.err;
+    RolloutArgs A;
+    unsigned grid = 0; int comm_ = 0, epw_ = 1;
+    int rc = fill_args(m, io, A, grid, comm_, epw_);
+    if (rc != 0 || io->bs == 0) return rc;
+    if (!io->adj_q_init || !io->adj_qd_init || !io->adj_refs) return PPR_E_ARG;
+    if (!io->adj_out_pos && !io->adj_out_vel && !io->adj_loss_pos) return PPR_E_ARG;      // nothing to differentiate
+    const bool reduce = io->adj_shared != nullptr;
+    if (reduce) {
+        if (!io->shared_params || !io->reduce_scratch ||
+            io->reduce_scratch_bytes < ppr_rollout_reduce_scratch_bytes(m, io->bs)) return PPR_E_WORKSPACE;
+    } else if (!io->adj_target_ke || !io->adj_target_kd || !io->adj_body_inv_mass || !io->adj_body_inertia ||
+               !io->adj_body_inv_inertia) return PPR_E_ARG;
+    A.adj_pos = io->adj_out_pos; A.adj_vel = io->adj_out_vel; A.adj_loss_pos = io->adj_loss_pos; A.saved_pos = io->out_pos;
+    A.adj_target_pos = io->adj_target_pos;
+    A.adj_q_init = io->adj_q_init; A.adj_qd_init = io->adj_qd_init; A.adj_torques = io->adj_torques;
+    A.adj_res_f = io->adj_res_f; A.adj_refs = io->adj_refs; A.adj_ke = io->adj_target_ke; A.adj_kd = io->adj_target_kd;
+    A.adj_inv_m = io->adj_body_inv_mass; A.adj_I = io->adj_body_inertia; A.adj_inv_I = io->adj_body_inv_inertia;
+    A.adj_partial = reduce ? (float*)io->reduce_scratch : nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = [&]() -> int {
+#ifndef PPR_AB_ONLY
+        if (m->ckpt_every > 1) PPR_LAUNCH_ROLLOUT(rollout_backward_kernel, true, , true);
+#endif
+        PPR_LAUNCH_ROLLOUT(rollout_backward_kernel, true, , false);
+    }();
+    if (rc != 0 || !reduce) return rc;
+    const int P = 2 * m->d.nqd + 19 * m->d.nb;
+    reduce_partials_kernel<<<(unsigned)((P + 31) / 32), dim3(32, 8), 0, st>>>((const float*)io->reduce_scratch, (int64_t)grid, P,
+                                                                             io->adj_shared);
     g_launches++;
     return (int)cudaGetLastError();
 }

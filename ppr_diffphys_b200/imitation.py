@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from .model import ASSET_DIR, load_robot
-from .ops import ForwardKinematics, ForwardWarp, FrameCompose, Se3Loss, SimEnv, convert_ppr_warp
+from .ops import ForwardKinematics, ForwardWarp, ForwardWarpLoss, FrameCompose, Se3Loss, SimEnv, convert_ppr_warp
 
 
 # ----------------------------------------------------------------------------------------- geometry (torch, xyzw)
@@ -145,8 +145,11 @@ _BULLET2GL = torch.tensor([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [1.0, 0.0, 0.0]])
 
 class ImitationModel(nn.Module):
     def __init__(self, robot="laikago", seqname="mi-trot", dt=5e-4, device="cuda", total_iters=101, lr=1e-4,
-                 traj_wt=0.01, pos_state_wt=0.01, vel_state_wt=1e-4, noise_std=2e-3, seed=0):
+                 traj_wt=0.01, pos_state_wt=0.01, vel_state_wt=1e-4, noise_std=2e-3, seed=0, fused_traj_loss=True):
         super().__init__()
+        # fused_traj_loss: the trajectory loss se3_loss(sim, target) (dp_model.py:777) is evaluated INSIDE the rollout
+        # kernels (ops.ForwardWarpLoss) instead of by a separate kernel pair on the frame poses
+        self.fused_traj_loss = bool(fused_traj_loss)
         self.device = torch.device(device)
         self.dt, self.noise_std = dt, noise_std
         self.wts = dict(traj=traj_wt, pos_state=pos_state_wt, vel_state=vel_state_wt)
@@ -292,8 +295,16 @@ class ImitationModel(nn.Module):
         inv_m = 1.0 / self.body_mass
         I = self.norm_body_inertia * self.body_mass[:, None, None]
         inv_I = self.norm_body_inertia_inv * inv_m[:, None, None]   # inverse(nI * m) = inverse(nI) / m
-        sim_position, sim_velocity = ForwardWarp.apply(q_init, qd_init, None, None, ref_ja, self.target_ke,
-                                                       self.target_kd, self.body_mass, inv_m, I, inv_I, self)
+        traj = None
+        if self.fused_traj_loss:
+            tgt = target_position.permute(1, 0, 2, 3).reshape(F, -1, 7)        # frame-major rows, like wp_pos
+            loss_pos, sim_position, sim_velocity = ForwardWarpLoss.apply(
+                q_init, qd_init, None, None, ref_ja, self.target_ke, self.target_kd, self.body_mass, inv_m, I, inv_I, tgt,
+                0.1, self)
+            traj = loss_pos.view(F, bs, -1).permute(1, 0, 2).mean(-1)          # [bs, F], mean over bodies
+        else:
+            sim_position, sim_velocity = ForwardWarp.apply(q_init, qd_init, None, None, ref_ja, self.target_ke,
+                                                           self.target_kd, self.body_mass, inv_m, I, inv_I, self)
         sim_velocity = convert_ppr_warp(sim_velocity)
         f2s = slice(0, None, self.steps_per_fr_interval)
         qq = queried_q[f2s].reshape(F, bs, -1)
@@ -303,7 +314,7 @@ class ImitationModel(nn.Module):
         sim_position = sim_position.reshape(F, bs, -1, 7).permute(1, 0, 2, 3)
         sim_velocity = sim_velocity.reshape(F, bs, -1, 6).permute(1, 0, 2, 3)
         loss_dict = {
-            "traj": reduce_loss(se3_loss(sim_position, target_position).mean(-1)),
+            "traj": reduce_loss(traj if traj is not None else se3_loss(sim_position, target_position).mean(-1)),
             "pos_state": reduce_loss(se3_loss(queried_position, sim_position.detach()).mean(-1)),
             "vel_state": reduce_loss(se3_loss(queried_velocity, sim_velocity.detach()).mean(-1)),
         }

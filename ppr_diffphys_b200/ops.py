@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._capi import make_desc
+from ._capi import RolloutIO, make_desc
 from .model import RobotModel, load_robot
 
 
@@ -323,6 +323,37 @@ class ForwardKinematics(torch.autograd.Function):
         return (gq if ctx.needs_input_grad[0] else None, gqd if ctx.needs_input_grad[1] else None, None)
 
 
+def _rollout_inputs(self, q_init, qd_init, torques, res_f, refs, target_ke, target_kd, body_inv_mass, body_inertia,
+                    body_inv_inertia):
+    """Shared preamble of the rollout Functions: geometry from the caller object, contiguous fp32 device tensors,
+    shared-parameter detection."""
+    env = self.env
+    dev = env.device
+    bs = int(self.num_envs)
+    nsteps = len(self.steps_idx)
+    f2s = list(self.frame2step)
+    stride = (f2s[1] - f2s[0]) if len(f2s) > 1 else nsteps
+    assert all(s == i * stride for i, s in enumerate(f2s)), "frame2step must be evenly strided"
+    a = dict(q_init=_f32c(q_init, dev), qd_init=_f32c(qd_init, dev), torques=_f32c(torques, dev),
+             res_f=_f32c(res_f, dev), refs=_f32c(refs, dev), ke=_f32c(target_ke, dev), kd=_f32c(target_kd, dev),
+             inv_m=_f32c(body_inv_mass, dev), I=_f32c(body_inertia, dev), inv_I=_f32c(body_inv_inertia, dev))
+    assert a["q_init"].numel() == bs * env.nq and a["qd_init"].numel() == bs * env.nqd
+    assert a["refs"].numel() == nsteps * bs * env.nqd
+    n_tab = env.joint_X_p.shape[0] // env.nb
+    assert n_tab in (1, bs), "per-env joint_X_p has %d blocks for %d envs" % (n_tab, bs)
+    # Extension of the reference signature: the five parameter tensors may be given UN-replicated
+    # ([nqd], [nqd], [nb], [nb,3,3], [nb,3,3]); the kernels then read one shared copy and the returned
+    # gradients are summed over envs (= the backward of dp_model.py:723-725's repeat()).
+    per_env = dict(ke=bs * env.nqd, kd=bs * env.nqd, inv_m=bs * env.nb, I=bs * env.nb * 9, inv_I=bs * env.nb * 9)
+    shared = all(a[k].numel() * bs == n for k, n in per_env.items()) and bs > 1
+    if not shared:
+        for k, n in per_env.items():
+            if a[k].numel() * bs == n and bs > 1:  # mixed: replicate the shared ones
+                a[k] = a[k].reshape(1, -1).expand(bs, -1).reshape(-1).contiguous()
+            assert a[k].numel() == n, "bad size for %s" % k
+    return env, dev, bs, nsteps, stride, a, shared
+
+
 class ForwardWarp(torch.autograd.Function):
     """``ForwardWarp.apply(q_init, qd_init, torques, res_f, refs, target_ke, target_kd, body_mass, body_inv_mass,
     body_inertia, body_inv_inertia, self) -> (wp_pos[F,bs*nb,7], wp_vel[F,bs*nb,6])`` -- dp_model.py:1145-1400.
@@ -335,30 +366,8 @@ class ForwardWarp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q_init, qd_init, torques, res_f, refs, target_ke, target_kd, body_mass, body_inv_mass,
                 body_inertia, body_inv_inertia, self):
-        env: SimEnv = self.env
-        dev = env.device
-        bs = int(self.num_envs)
-        nsteps = len(self.steps_idx)
-        f2s = list(self.frame2step)
-        stride = (f2s[1] - f2s[0]) if len(f2s) > 1 else nsteps
-        assert all(s == i * stride for i, s in enumerate(f2s)), "frame2step must be evenly strided"
-        a = dict(q_init=_f32c(q_init, dev), qd_init=_f32c(qd_init, dev), torques=_f32c(torques, dev),
-                 res_f=_f32c(res_f, dev), refs=_f32c(refs, dev), ke=_f32c(target_ke, dev), kd=_f32c(target_kd, dev),
-                 inv_m=_f32c(body_inv_mass, dev), I=_f32c(body_inertia, dev), inv_I=_f32c(body_inv_inertia, dev))
-        assert a["q_init"].numel() == bs * env.nq and a["qd_init"].numel() == bs * env.nqd
-        assert a["refs"].numel() == nsteps * bs * env.nqd
-        n_tab = env.joint_X_p.shape[0] // env.nb
-        assert n_tab in (1, bs), "per-env joint_X_p has %d blocks for %d envs" % (n_tab, bs)
-        # Extension of the reference signature: the five parameter tensors may be given UN-replicated
-        # ([nqd], [nqd], [nb], [nb,3,3], [nb,3,3]); the kernels then read one shared copy and the returned
-        # gradients are summed over envs (= the backward of dp_model.py:723-725's repeat()).
-        per_env = dict(ke=bs * env.nqd, kd=bs * env.nqd, inv_m=bs * env.nb, I=bs * env.nb * 9, inv_I=bs * env.nb * 9)
-        shared = all(a[k].numel() * bs == n for k, n in per_env.items()) and bs > 1
-        if not shared:
-            for k, n in per_env.items():
-                if a[k].numel() * bs == n and bs > 1:  # mixed: replicate the shared ones
-                    a[k] = a[k].reshape(1, -1).expand(bs, -1).reshape(-1).contiguous()
-                assert a[k].numel() == n, "bad size for %s" % k
+        env, dev, bs, nsteps, stride, a, shared = _rollout_inputs(self, q_init, qd_init, torques, res_f, refs, target_ke,
+                                                                  target_kd, body_inv_mass, body_inertia, body_inv_inertia)
         want_forces = bool(getattr(self, "record_forces", True))
         pos, vel, grf, jaf, ws = env.rollout_forward(bs, nsteps, stride, float(self.dt), a["q_init"], a["qd_init"],
                                                      a["torques"], a["res_f"], a["refs"], a["ke"], a["kd"],
@@ -499,3 +508,112 @@ class RefsFromFrames(torch.autograd.Function):
             _lib.check(_lib.lib().ppr_refs_from_frames_backward(T, stride, F, n, _ptr(a), _ptr(adj), _stream()),
                        "ppr_refs_from_frames_backward")
         return adj, None, None
+
+
+def _addr(t):
+    return None if t is None else t.data_ptr()
+
+
+class ForwardWarpLoss(torch.autograd.Function):
+    """``ForwardWarpLoss.apply(q_init, qd_init, torques, res_f, refs, target_ke, target_kd, body_mass, body_inv_mass,
+    body_inertia, body_inv_inertia, target_pos[F, bs*nb, 7], rot_ratio, self) -> (loss_pos[F, bs*nb], wp_pos, wp_vel)``
+
+    ForwardWarp with the imitation objective's pose loss FUSED into the rollout:
+    ``loss_pos = se3_loss(wp_pos, target_pos, rot_ratio)`` per body and frame (dp_model.py:777, dp_utils.py:113-138) is
+    evaluated by the forward kernel while the pose is in registers, and the adjoint kernel seeds itself from
+    ``d objective / d loss_pos`` -- no ``adj_pos`` tensor, no separate loss kernels; the gradient w.r.t. ``target_pos``
+    (the targets depend on ``global_q``) is written by the adjoint kernel as well.  The caller applies its own mean /
+    masking / clipping (``reduce_loss``) to ``loss_pos``.  ``wp_pos`` / ``wp_vel`` are returned for the terms that use the
+    simulated states detached (dp_model.py:794,800) and for ``sim_trajs``; they carry NO gradient here."""
+
+    @staticmethod
+    def forward(ctx, q_init, qd_init, torques, res_f, refs, target_ke, target_kd, body_mass, body_inv_mass, body_inertia,
+                body_inv_inertia, target_pos, rot_ratio, self):
+        env, dev, bs, nsteps, stride, a, shared = _rollout_inputs(self, q_init, qd_init, torques, res_f, refs, target_ke,
+                                                                  target_kd, body_inv_mass, body_inertia, body_inv_inertia)
+        F = (nsteps - 1) // stride + 1
+        tgt = _f32c(target_pos, dev)
+        assert tgt.numel() == F * bs * env.nb * 7, "target_pos must be [F, bs*nb, 7]"
+        e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        want_forces = bool(getattr(self, "record_forces", True))
+        pos, vel, loss = e(F, bs * env.nb, 7), e(F, bs * env.nb, 6), e(F, bs * env.nb)
+        grf = e(F, bs * env.nb, 6) if want_forces else None
+        jaf = e(F, bs * env.nb, 6) if want_forces else None
+        ws = e((env.workspace_bytes(bs, nsteps) + 3) // 4)
+        io = RolloutIO()
+        io.bs, io.nsteps, io.frame_stride, io.dt, io.shared_params = bs, nsteps, stride, float(self.dt), int(shared)
+        for k, v in (("q_init", a["q_init"]), ("qd_init", a["qd_init"]), ("torques", a["torques"]), ("res_f", a["res_f"]),
+                     ("refs", a["refs"]), ("target_ke", a["ke"]), ("target_kd", a["kd"]), ("body_inv_mass", a["inv_m"]),
+                     ("body_inertia", a["I"]), ("body_inv_inertia", a["inv_I"]), ("out_pos", pos), ("out_vel", vel),
+                     ("out_grf", grf), ("out_jaf", jaf), ("workspace", ws), ("target_pos", tgt), ("loss_pos", loss)):
+            setattr(io, k, _addr(v))
+        io.workspace_bytes, io.rot_ratio = ws.numel() * 4, float(rot_ratio)
+        with torch.cuda.device(dev):
+            _lib.check(env._lib.ppr_rollout_forward_ex(env._h, C.byref(io), _stream()), "ppr_rollout_forward_ex")
+        self.grfs = [grf[i] for i in range(F)] if want_forces else []
+        self.jafs = [jaf[i] for i in range(F)] if want_forces else []
+        self.sim_trajs = LazyFrames(pos[:, : env.nb])
+        ctx.env, ctx.a, ctx.keep, ctx.shared, ctx.snap = env, a, (pos, vel, ws, tgt), shared, env._snapshot()
+        ctx.dims = (bs, nsteps, stride, float(self.dt), float(rot_ratio))
+        ctx.shapes = dict(q_init=q_init.shape, qd_init=qd_init.shape, refs=refs.shape,
+                          torques=None if torques is None else torques.shape,
+                          res_f=None if res_f is None else res_f.shape, ke=target_ke.shape, kd=target_kd.shape,
+                          mass=body_mass.shape, inv_m=body_inv_mass.shape, I=body_inertia.shape, inv_I=body_inv_inertia.shape,
+                          target=target_pos.shape)
+        ctx.mark_non_differentiable(pos, vel)
+        return loss, pos, vel
+
+    @staticmethod
+    def backward(ctx, adj_loss, _adj_pos, _adj_vel):
+        env, a = ctx.env, ctx.a
+        bs, nsteps, stride, dt, rot_ratio = ctx.dims
+        if env._snapshot() != ctx.snap:
+            raise _lib.PprError("SimEnv was modified between ForwardWarpLoss.forward and .backward")
+        pos, vel, ws, tgt = ctx.keep
+        dev, nb, nq, nqd = env.device, env.nb, env.nq, env.nqd
+        e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+        al = _f32c(adj_loss, dev)
+        g = dict(q_init=e(bs * nq), qd_init=e(bs * nqd), refs=e(nsteps, bs * nqd),
+                 torques=e(nsteps, bs * nqd) if a["torques"] is not None else None,
+                 res_f=e(nsteps, bs * nb, 6) if a["res_f"] is not None else None)
+        io = RolloutIO()
+        io.bs, io.nsteps, io.frame_stride, io.dt, io.shared_params = bs, nsteps, stride, dt, int(ctx.shared)
+        keep = []
+        if ctx.shared:
+            P = 2 * nqd + 19 * nb
+            packed = e(P)
+            scratch = e((int(env._lib.ppr_rollout_reduce_scratch_bytes(env._h, bs)) + 3) // 4)
+            io.adj_shared, io.reduce_scratch, io.reduce_scratch_bytes = packed.data_ptr(), scratch.data_ptr(), scratch.numel() * 4
+            g.update(target_ke=packed[:nqd], target_kd=packed[nqd:2 * nqd], body_inv_mass=packed[2 * nqd:2 * nqd + nb],
+                     body_inertia=packed[2 * nqd + nb:2 * nqd + 10 * nb].view(nb, 3, 3),
+                     body_inv_inertia=packed[2 * nqd + 10 * nb:].view(nb, 3, 3))
+            keep += [packed, scratch]
+        else:
+            g.update(target_ke=e(bs * nqd), target_kd=e(bs * nqd), body_inv_mass=e(bs * nb), body_inertia=e(bs * nb, 3, 3),
+                     body_inv_inertia=e(bs * nb, 3, 3))
+            for k, f in (("target_ke", "adj_target_ke"), ("target_kd", "adj_target_kd"), ("body_inv_mass", "adj_body_inv_mass"),
+                         ("body_inertia", "adj_body_inertia"), ("body_inv_inertia", "adj_body_inv_inertia")):
+                setattr(io, f, g[k].data_ptr())
+        for k, v in (("q_init", a["q_init"]), ("qd_init", a["qd_init"]), ("torques", a["torques"]), ("res_f", a["res_f"]),
+                     ("refs", a["refs"]), ("target_ke", a["ke"]), ("target_kd", a["kd"]), ("body_inv_mass", a["inv_m"]),
+                     ("body_inertia", a["I"]), ("body_inv_inertia", a["inv_I"]), ("out_pos", pos), ("out_vel", vel),
+                     ("workspace", ws), ("target_pos", tgt), ("adj_loss_pos", al), ("adj_q_init", g["q_init"]),
+                     ("adj_qd_init", g["qd_init"]), ("adj_torques", g["torques"]), ("adj_res_f", g["res_f"]),
+                     ("adj_refs", g["refs"])):
+            setattr(io, k, _addr(v))
+        io.workspace_bytes, io.rot_ratio = ws.numel() * 4, rot_ratio
+        g_tgt = None
+        if ctx.needs_input_grad[11]:     # the targets depend on global_q (and on the root-pose net through FK)
+            g_tgt = torch.empty_like(tgt)
+            io.adj_target_pos = g_tgt.data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(env._lib.ppr_rollout_backward_ex(env._h, C.byref(io), _stream()), "ppr_rollout_backward_ex")
+        need, sh = ctx.needs_input_grad, ctx.shapes
+        pick = lambda i, t, shape: None if (not need[i] or t is None) else t.reshape(shape)
+        body_mass_grad = torch.zeros(sh["mass"], device=dev) if need[7] else None  # K5 never reads m
+        return (pick(0, g["q_init"], sh["q_init"]), pick(1, g["qd_init"], sh["qd_init"]),
+                pick(2, g["torques"], sh["torques"]), pick(3, g["res_f"], sh["res_f"]), pick(4, g["refs"], sh["refs"]),
+                pick(5, g["target_ke"], sh["ke"]), pick(6, g["target_kd"], sh["kd"]), body_mass_grad,
+                pick(8, g["body_inv_mass"], sh["inv_m"]), pick(9, g["body_inertia"], sh["I"]),
+                pick(10, g["body_inv_inertia"], sh["inv_I"]), None if g_tgt is None else g_tgt.reshape(sh["target"]), None,
+                None)

@@ -163,3 +163,37 @@ def test_fused_frame_compose_matches_composed_torch_functions():
     assert torch.allclose(out[0][2], out[1][2], rtol=2e-4, atol=1e-2)      # sums of 7600 float32 terms
     assert torch.isfinite(out[1][3]).all()
     assert float((out[0][3] - out[1][3]).abs().max() / out[0][3].abs().max()) < 1e-5
+
+
+def test_fused_trajectory_loss_matches_the_separate_loss_kernels():
+    """ForwardWarpLoss (pose loss evaluated inside the rollout kernels, adjoint seeded in-kernel) == ForwardWarp followed
+    by the se3 loss on the frame poses: same loss values, same gradients of every trainable parameter."""
+    import numpy as np
+    from ppr_diffphys_b200.imitation import ImitationModel
+    out = {}
+    for fused in (False, True):
+        torch.manual_seed(0)
+        m = ImitationModel("laikago", "mi-pace", total_iters=11, seed=3, fused_traj_loss=fused)
+        m.train()
+        m.reinit_envs(6, frames_per_wdw=5)
+        # make the control nets non-trivial (their heads start at zero)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.dim() == 2 and p.shape[0] <= 64:
+                    p.add_(torch.randn(p.shape, device=p.device, generator=g) * 1e-3)
+        fs = torch.tensor([0.0, 3.0, 7.0, 11.0, 20.0, 30.0], device="cuda")
+        noise = torch.zeros(6, m.env.nq, device="cuda")
+        losses = m.forward(frame_start=fs, noise=noise)
+        m.optimizer.zero_grad(set_to_none=True)
+        losses["total_loss"].backward()
+        out[fused] = ({k: float(v) for k, v in losses.items()},
+                      {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None})
+    l0, g0 = out[False]
+    l1, g1 = out[True]
+    for k in l0:
+        assert abs(l0[k] - l1[k]) <= 1e-6 * max(1.0, abs(l0[k])), (k, l0[k], l1[k])
+    assert set(g0) == set(g1) and len(g0) > 10
+    for n in g0:
+        d = float((g0[n] - g1[n]).norm()) / (float(g0[n].norm()) + 1e-12)
+        assert d <= 2e-4, (n, d)
