@@ -52,7 +52,9 @@ template <int JM> struct RowOf { static constexpr int kQuads = JM == JM_REVOLUTE
 #define PPR_BLOCK 128  // FK kernels (warp layout)
 #define PPR_SUP_N 16   // cells per edge of a cube-map face of the support-function table
 #define PPR_SUP_FLOATS (6 * (PPR_SUP_N + 1) * (PPR_SUP_N + 1))
+#ifndef PPR_CLIST_CAP
 #define PPR_CLIST_CAP 16  // penetrating points listed per body before falling back to the cooperative path
+#endif
 #define PPR_CLIST_STRIDE (PPR_CLIST_CAP + 1)
 #ifndef PPR_BODY_MAJOR
 #define PPR_BODY_MAJOR 1
@@ -230,7 +232,7 @@ template <int RQ, bool BULK> struct RowStream {
 //   gather_*  : each thread sums a message held by the threads of its child bodies
 // `child` packs up to 8 children as bytes: slot of the child + 1 (0 = none);
 // `ps` = slot of the parent (own slot if none).
-template <int NT> struct WarpComm {
+template <int NT, bool ADJ = true> struct WarpComm {
     static constexpr int kThreads = NT;
     static constexpr bool kBlock = false;
     static constexpr int kExFloats = 0;
@@ -282,13 +284,15 @@ template <int NT> struct WarpComm {
 // a gather_* call (different areas `ex` / `msg`), which makes the single barrier per call sufficient: every read of
 // an area happens before the next barrier, every write to it after one more barrier. parent_body / parent_vec are
 // used back to back (FK levels) and therefore carry a trailing barrier.
-template <int NT> struct BlockComm {
+template <int NT, bool ADJ = true> struct BlockComm {
     static constexpr int kThreads = NT;
     static constexpr bool kBlock = true;
     // exchange areas are arrays of float4 [k][NT] (thread t's k-th quad at [k * NT + t]): one LDS.128 / STS.128 moves
-    // what four scalar accesses did, conflict-free because consecutive threads touch consecutive 16-byte slots
-    static constexpr int kExQuads = 6;   // body 13 + world COM 3 = 4 quads, wrench 6 (+2 pad) = 2 quads
-    static constexpr int kMsgQuads = 4;  // body 13 (+3 pad) or wrench 6 (+2 pad)
+    // what four scalar accesses did, conflict-free because consecutive threads touch consecutive 16-byte slots.
+    // The forward kernel exchanges less (state down, wrench up) than the adjoint (state + wrench adjoint down, body
+    // adjoint up): 6 instead of 10 quads per thread, which is 6 kB per block given back to the L1 cache.
+    static constexpr int kExQuads = ADJ ? 6 : 4;   // body 13 + world COM 3 = 4 quads (+ wrench adjoint 6 (+2 pad) = 2 quads)
+    static constexpr int kMsgQuads = ADJ ? 4 : 2;  // body adjoint 13 (+3 pad) / wrench 6 (+2 pad)
     static constexpr int kExFloats = (kExQuads + kMsgQuads) * 4 * NT + 4;  // + two 8-byte mbarriers
     float4* ex;
     float4* msg;
@@ -953,6 +957,26 @@ __device__ __forceinline__ void store_wrench_row(float* base, const WrenchF& w) 
     base[0] = w.t.x; base[1] = w.t.y; base[2] = w.t.z; base[3] = w.f.x; base[4] = w.f.y; base[5] = w.f.z;
 }
 
+// Fused pose loss at a frame step (ppr_loss.h).  Out of line on purpose: it runs once per frame, not per substep, and
+// the time loops of the COMPOUND adjoint already fill the instruction cache.
+__device__ __noinline__ float frame_pose_loss(const float* pose, const float* target, float ratio) {
+    const float pp[7] = {pose[0], pose[1], pose[2], pose[3], pose[4], pose[5], pose[6]};
+    const float gg[7] = {target[0], target[1], target[2], target[3], target[4], target[5], target[6]};
+    return se3_pair_loss<float>(7, pp, gg, ratio, 1e-4f);
+}
+__device__ __noinline__ void frame_pose_loss_adj(const float* pose, const float* target, float ratio, float adj, float* ap,
+                                                 float* adj_target) {
+    const float pp[7] = {pose[0], pose[1], pose[2], pose[3], pose[4], pose[5], pose[6]};
+    const float gg[7] = {target[0], target[1], target[2], target[3], target[4], target[5], target[6]};
+    float ag[7];
+    se3_pair_loss_adj<float>(7, pp, gg, ratio, 1e-4f, adj, ap, adj_target ? ag : (float*)nullptr);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        ap[k] = nan0(ap[k]);
+        if (adj_target) adj_target[k] = nan0(ag[k]);
+    }
+}
+
 // Forces of one substep in two halves.  forces_pre: contacts + this body's joint, ends by PUBLISHING the wrench the
 // joint exerts on the parent; forces_post: adds the wrenches of the body's children -> F = total wrench on this lane's
 // body.  Work that does not need the children's wrenches goes between the two (split-phase rendezvous).
@@ -1092,12 +1116,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
             o[0] = s.x.x; o[1] = s.x.y; o[2] = s.x.z; o[3] = s.r.x; o[4] = s.r.y; o[5] = s.r.z; o[6] = s.r.w;
             float* v = A.out_vel + frow * 6;
             v[0] = s.w.x; v[1] = s.w.y; v[2] = s.w.z; v[3] = s.v.x; v[4] = s.v.y; v[5] = s.v.z;
-            if (A.loss_pos) {
-                const float* tg = A.target_pos + frow * 7;
-                const float pp[7] = {s.x.x, s.x.y, s.x.z, s.r.x, s.r.y, s.r.z, s.r.w};
-                const float gg[7] = {tg[0], tg[1], tg[2], tg[3], tg[4], tg[5], tg[6]};
-                A.loss_pos[frow] = se3_pair_loss<float>(7, pp, gg, A.rot_ratio, 1e-4f);
-            }
+            if (A.loss_pos) A.loss_pos[frow] = frame_pose_loss(o, A.target_pos + frow * 7, A.rot_ratio);
         }
         // the substep past the last frame exists only for the force side channels (dp_model.py:397): skip it
         // when nobody asked for them
@@ -1232,20 +1251,11 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
                 adjN.v += v3<float>(b[3], b[4], b[5]);
             }
             if (A.adj_loss_pos) {   // fused pose loss: d loss / d pose from the saved frame pose and the target
-                const float* sp = A.saved_pos + frow * 7;
-                const float* tg = A.target_pos + frow * 7;
-                const float pp[7] = {sp[0], sp[1], sp[2], sp[3], sp[4], sp[5], sp[6]};
-                const float gg[7] = {tg[0], tg[1], tg[2], tg[3], tg[4], tg[5], tg[6]};
-                float ap[7], ag[7];
-                se3_pair_loss_adj<float>(7, pp, gg, A.rot_ratio, 1e-4f, A.adj_loss_pos[frow], ap,
-                                         A.adj_target_pos ? ag : (float*)nullptr);
-                if (A.adj_target_pos) {
-                    float* o = A.adj_target_pos + frow * 7;
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) o[k] = nan0(ag[k]);
-                }
-                adjN.x += v3<float>(nan0(ap[0]), nan0(ap[1]), nan0(ap[2]));
-                adjN.r += q4<float>(nan0(ap[3]), nan0(ap[4]), nan0(ap[5]), nan0(ap[6]));
+                float ap[7];
+                frame_pose_loss_adj(A.saved_pos + frow * 7, A.target_pos + frow * 7, A.rot_ratio, A.adj_loss_pos[frow], ap,
+                                    A.adj_target_pos ? A.adj_target_pos + frow * 7 : nullptr);
+                adjN.x += v3<float>(ap[0], ap[1], ap[2]);
+                adjN.r += q4<float>(ap[3], ap[4], ap[5], ap[6]);
             }
         }
         if (t == 0) break;
@@ -1800,7 +1810,7 @@ template <class K> static cudaError_t launch_rollout(K kernel, size_t smem, unsi
         cudaError_t e_ = cudaErrorInvalidValue;                                                                      \
         DevModel d_ = m->d;                                                                                          \
         d_.epw = epw_;                                                                                               \
-        typedef BlockComm<PPR_NT1> C_;                                                                               \
+        typedef BlockComm<PPR_NT1, ADJ> C_;                                                                          \
         if (comm_ == 1 && m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, PPR_NT1, st, d_, A); \
         else if (comm_ == 1 && m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, PPR_NT1, st, d_, A); \
         g_launches++;                                                                                                \
@@ -1813,17 +1823,17 @@ template <class K> static cudaError_t launch_rollout(K kernel, size_t smem, unsi
         DevModel d_ = m->d;                                                                                          \
         d_.epw = epw_;                                                                                               \
         if (comm_ == 0) {                                                                                            \
-            typedef WarpComm<128> C_;                                                                                \
+            typedef WarpComm<128, ADJ> C_;                                                                           \
             if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, d_, A); \
             else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, d_, A); \
             else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, d_, A); \
         } else if (comm_ == 1) {                                                                                     \
-            typedef BlockComm<PPR_NT1> C_;                                                                             \
+            typedef BlockComm<PPR_NT1, ADJ> C_;                                                                        \
             if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, PPR_NT1, st, d_, A); \
             else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, PPR_NT1, st, d_, A); \
             else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, PPR_NT1, st, d_, A); \
         } else {                                                                                                     \
-            typedef BlockComm<160> C_;                                                                               \
+            typedef BlockComm<160, ADJ> C_;                                                                          \
             if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, d_, A); \
             else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, d_, A); \
             else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 160, st, d_, A); \
