@@ -1440,19 +1440,27 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     }
 }
 
-// rows[R][P] -> out[P], fixed summation order (deterministic): 32 columns x 8 row lanes per block
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ rows, int64_t R, int P,
-                                                              float* __restrict__ out) {
-    __shared__ float part[8][33];
+// rows[R][P] -> out[P], fixed summation order (deterministic): 32 columns x 32 row lanes per block, four independent
+// partial sums per thread (the loop is latency bound: R is ~10^4 rows of ~300 floats for a full batch)
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ rows, int64_t R, int P,
+                                                               float* __restrict__ out) {
+    __shared__ float part[32][33];
     const int col = blockIdx.x * 32 + threadIdx.x;
-    float s = 0.f;
-    if (col < P) for (int64_t r = threadIdx.y; r < R; r += 8) s += rows[r * P + col];
-    part[threadIdx.y][threadIdx.x] = s;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (col < P) {
+        int64_t r = threadIdx.y;
+        for (; r + 96 < R; r += 128) {
+            s0 += rows[r * P + col]; s1 += rows[(r + 32) * P + col];
+            s2 += rows[(r + 64) * P + col]; s3 += rows[(r + 96) * P + col];
+        }
+        for (; r < R; r += 32) s0 += rows[r * P + col];
+    }
+    part[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (threadIdx.y == 0 && col < P) {
         float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+        for (int k = 0; k < 32; ++k) t += part[k][threadIdx.x];
         out[col] = t;
     }
 }
@@ -1992,7 +2000,7 @@ extern "C" int ppr_rollout_backward_shared(ppr_model_t m, int64_t bs, int64_t ns
     }();
     if (rc != 0) return rc;
     const int P = 2 * m->d.nqd + 19 * m->d.nb;
-    reduce_partials_kernel<<<(unsigned)((P + 31) / 32), dim3(32, 8), 0, st>>>((const float*)scratch, (int64_t)grid, P, adj_shared);
+    reduce_partials_kernel<<<(unsigned)((P + 31) / 32), dim3(32, 32), 0, st>>>((const float*)scratch, (int64_t)grid, P, adj_shared);
     g_launches++;
     return (int)cudaGetLastError();
 }
@@ -2063,7 +2071,7 @@ extern "C" int ppr_rollout_backward_ex(ppr_model_t m, const ppr_rollout_io* io, 
     }();
     if (rc != 0 || !reduce) return rc;
     const int P = 2 * m->d.nqd + 19 * m->d.nb;
-    reduce_partials_kernel<<<(unsigned)((P + 31) / 32), dim3(32, 8), 0, st>>>((const float*)io->reduce_scratch, (int64_t)grid, P,
+    reduce_partials_kernel<<<(unsigned)((P + 31) / 32), dim3(32, 32), 0, st>>>((const float*)io->reduce_scratch, (int64_t)grid, P,
                                                                              io->adj_shared);
     g_launches++;
     return (int)cudaGetLastError();

@@ -415,8 +415,11 @@ def test_latency_layout_equals_throughput_layout(robot):
     # (joint forces amplify a last-bit pose difference by the 8e3..1.6e4 N/m attachment stiffness)
     for name, tol, x, y in zip(("pos", "vel", "grf", "jaf"), (2e-6, 2e-6, 1e-4, 1e-4), out[0][:4], out[1][:4]):
         assert rel(x, y.double().cpu()) < tol, (name, rel(x, y.double().cpu()))
+    # gradients: 1e-5, except laikago in stiff contact where last-bit differences between two compilations are amplified
+    # like every other rounding difference (fp32 noise floor of that fixture: 1e-3 .. 5e-3, tests/test_oracle.py)
+    gtol = 1e-4 if robot == "laikago" else 1e-5
     for k, x, y in zip(KEYS, out[0][4], out[1][4]):
-        assert rel(x, y.double().cpu()) < 1e-5, k
+        assert rel(x, y.double().cpu()) < gtol, (k, rel(x, y.double().cpu()))
 
 
 def test_single_frame_window_and_single_env():

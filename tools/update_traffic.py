@@ -43,9 +43,10 @@ def main():
         rd = float(r[col("dram__bytes_read.sum")]) * unit_scale[units[col("dram__bytes_read.sum")]]
         wr = float(r[col("dram__bytes_write.sum")]) * unit_scale[units[col("dram__bytes_write.sum")]]
         entry[key] = int(rd + wr)
-        f = lambda n: float(r[col(n)]) if n in hdr else 0.0
-        flops = 2 * f("smsp__sass_thread_inst_executed_op_ffma_pred_on.sum") + f("smsp__sass_thread_inst_executed_op_fadd_pred_on.sum") \
-            + f("smsp__sass_thread_inst_executed_op_fmul_pred_on.sum")
+        # the raw page holds these as per-cycle rates summed over the SMSPs: x elapsed SMSP cycles = thread instructions
+        cyc = float(r[col("smsp__cycles_elapsed.avg")]) if "smsp__cycles_elapsed.avg" in hdr else float(r[col("sm__cycles_elapsed.avg")])
+        f = lambda op: float(r[col("smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % op)]) * cyc
+        flops = 2 * f("ffma") + f("fadd") + f("fmul")
         entry["fp32_flops_per_env_step"][key] = int(round(flops / env_steps))
     tj[workload] = entry
     json.dump(tj, open(path, "w"), indent=1)
