@@ -40,6 +40,8 @@ def main():
     step = None if args.no_graph else GraphedStep(model)
     for it in range(args.iters):
         model.progress = it / max(1, args.iters - 1)
+        if it % 20 == 0:
+            model.save_checkpoint()     # main.py:73-74: every iters_per_round iterations (in-memory roll-back queue)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         if step is not None:

@@ -8,7 +8,8 @@ method names and data flow for the part that feeds and consumes the simulator bo
 
 and the same learnable quantities (control-reference networks, PD gains, body mass, global SE(3), initial velocity).
 What is deliberately NOT mirrored (out of the hot-path scope): visualiser / ``query()`` mesh
-articulation, lab4d coupling, in-memory checkpoint roll-back, per-parameter median gradient clipping.
+articulation, lab4d coupling, per-parameter median gradient clipping, checkpoint files on disk (the in-memory
+queue and its roll-back are mirrored: save_checkpoint / update).
 Differences that matter for speed: mocap interpolation runs in torch on the device (the reference calls scipy on
 the CPU every step, :605-609); shared parameters are passed UN-replicated to ``ForwardWarp`` (the reference
 replicates + inverts bs*nb 3x3 matrices per step, :723-730).
@@ -78,10 +79,21 @@ def se3_loss(pred, gt, rot_ratio=0.1):
     return Se3Loss.apply(pred, gt.to(pred.device), rot_ratio)
 
 
-def reduce_loss(loss_seq):
-    """dp_utils.py:93-110 without the trajectory clipping branch: mean over the entries > 0 (all entries when none
-    is).  Written as a masked mean -- no boolean indexing, no host read -- so the step can be captured in a CUDA
-    graph; identical because the se3 losses are >= 0 (no entry > 0  <=>  every entry is 0  <=>  both means are 0)."""
+def reduce_loss(loss_seq, clip=False):
+    """dp_utils.py:93-110 on a [bs, T] loss: optional trajectory clipping, then the mean over the entries > 0 (all
+    entries when none is).  Written with masks -- no boolean indexing, no Python loop over envs, no host read -- so the
+    step can be captured in a CUDA graph.
+
+    clip (used for the trajectory loss, dp_model.py:779): the threshold is 10 x the median of the positive entries of
+    env 0 (the reference computes it in the first loop iteration and keeps it for all envs, :98-100); every env is cut
+    from its first entry above the threshold onwards (:101-103).  The masked mean is identical to the reference's
+    because the se3 losses are >= 0 (no entry > 0  <=>  every entry is 0  <=>  both means are 0)."""
+    if clip:
+        first = loss_seq[0]
+        th = torch.nanmedian(torch.where(first > 0, first, torch.full_like(first, float("nan")))) * 10
+        over = (loss_seq > th).to(loss_seq.dtype)           # (a NaN threshold -- no positive entry -- clips nothing)
+        cut = torch.cumsum(over, dim=1) > 0                 # at or after the first entry above the threshold
+        loss_seq = torch.where(cut, torch.zeros_like(loss_seq), loss_seq)
     pos = loss_seq > 0
     return torch.where(pos, loss_seq, torch.zeros_like(loss_seq)).sum() / pos.sum().clamp_min(1)
 
@@ -314,7 +326,7 @@ class ImitationModel(nn.Module):
         sim_position = sim_position.reshape(F, bs, -1, 7).permute(1, 0, 2, 3)
         sim_velocity = sim_velocity.reshape(F, bs, -1, 6).permute(1, 0, 2, 3)
         loss_dict = {
-            "traj": reduce_loss(traj if traj is not None else se3_loss(sim_position, target_position).mean(-1)),
+            "traj": reduce_loss(traj if traj is not None else se3_loss(sim_position, target_position).mean(-1), clip=True),
             "pos_state": reduce_loss(se3_loss(queried_position, sim_position.detach()).mean(-1)),
             "vel_state": reduce_loss(se3_loss(queried_velocity, sim_velocity.detach()).mean(-1)),
         }
@@ -326,14 +338,32 @@ class ImitationModel(nn.Module):
     def backward(self, loss):
         loss.backward()
 
+    def save_checkpoint(self):
+        """In-memory queue of length two of (model, optimizer, scheduler) states (dp_model.py:912-921; the reference
+        also writes ckpt_phys_%04d.pth, which is out of scope here).  main.py calls it every `iters_per_round` iterations."""
+        from copy import deepcopy
+        if not hasattr(self, "_cache"):
+            self._cache = [None, None]
+        self._cache[0] = self._cache[1]
+        self._cache[1] = (deepcopy(self.state_dict()), deepcopy(self.optimizer.state_dict()),
+                          deepcopy(self.scheduler.state_dict()))
+
     def update(self, thresh=10.0, keep_grads=False):
-        """clip, sanity-check and apply the gradients (dp_model.py:511-548,936-963 without the roll-back): an
-        iteration whose gradient norm is non-finite or above ``thresh`` is skipped (the reference drops the gradients,
-        which makes its optimizer step a no-op).  ``keep_grads``: leave the .grad tensors in place (GraphedStep
-        re-fills the same memory on the next replay)."""
+        """clip, sanity-check and apply the gradients (dp_model.py:511-548,936-963): an iteration whose gradient norm
+        is non-finite or above ``thresh`` is skipped (the reference drops the gradients, which makes its optimizer step
+        a no-op) and the model / optimizer / scheduler roll back to the snapshot of two rounds ago when there is one
+        (:947-952).  ``keep_grads``: leave the .grad tensors in place (GraphedStep re-fills the same memory on the
+        next replay)."""
         params = [p for g in self.optimizer.param_groups for p in g["params"] if p.grad is not None]
         grad_norm = torch.nn.utils.clip_grad_norm_(params, thresh)
         skipped = bool(not torch.isfinite(grad_norm) or grad_norm > thresh)
+        if skipped and getattr(self, "_cache", [None])[0] is not None:
+            sd, od, sch = self._cache[0]
+            with torch.no_grad():                            # in place: parameter storage (and a captured graph) stay valid
+                for k, v in self.state_dict().items():
+                    v.copy_(sd[k])
+            self.optimizer.load_state_dict(od)
+            self.scheduler.load_state_dict(sch)
         if not skipped:
             self.optimizer.step()
         self.scheduler.step()

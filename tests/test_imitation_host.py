@@ -202,3 +202,33 @@ def test_frame_compose_adjoint_f64_equals_autograd():
     assert np.abs(T - t.detach().numpy()).max() < 1e-13 and np.abs(U - u.detach().numpy()).max() < 1e-13
     assert np.abs(ag.sum(0) - gq.grad.numpy()).max() < 1e-11
     assert np.abs(ad - d.grad.numpy()).max() < 1e-12
+
+
+def test_reduce_loss_clipping_matches_the_reference_loop():
+    """Masked / graph-capturable reduce_loss(clip=True) == a literal re-statement of dp_utils.py:93-110 (threshold from
+    env 0, every env cut from its first entry above it, mean over the positive entries)."""
+    from ppr_diffphys_b200.imitation import reduce_loss
+
+    def literal(loss_seq):
+        loss_seq = loss_seq.clone()
+        th = 0
+        for i in range(len(loss_seq)):
+            if th == 0:
+                sub = loss_seq[i]
+                th = sub[sub > 0].median() * 10
+            clip_val, clip_idx = torch.max(loss_seq[i] > th, 0)
+            if clip_val == 1:
+                loss_seq[i, clip_idx:] = 0
+        return loss_seq[loss_seq > 0].mean() if loss_seq.sum() > 0 else loss_seq.mean()
+
+    g = torch.Generator().manual_seed(0)
+    for trial in range(20):
+        x = torch.rand(6, 9, generator=g) * 0.01
+        if trial % 2:
+            x[torch.randint(0, 6, (1,), generator=g), torch.randint(0, 9, (1,), generator=g)] = 5.0    # a diverged window
+        if trial % 3 == 0:
+            x[:, 0] = 0                                                                                # masked (out-of-seq) entries
+        assert torch.allclose(reduce_loss(x, clip=True), literal(x), rtol=1e-6, atol=0), trial
+        assert torch.allclose(reduce_loss(x), x[x > 0].mean())
+    z = torch.zeros(3, 4)
+    assert float(reduce_loss(z, clip=True)) == 0.0 and float(reduce_loss(z)) == 0.0
