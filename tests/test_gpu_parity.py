@@ -463,6 +463,49 @@ def test_c_abi_error_codes(monkeypatch):
     before = _lib.launch_count()
     env.fk(torch.zeros(3, env.nq, device="cuda"), torch.zeros(3, env.nqd, device="cuda"))
     assert _lib.launch_count() == before + 1
+    # struct-argument entry points (ppr_rollout_io)
+    from ppr_diffphys_b200._capi import RolloutIO
+    assert lib.ppr_rollout_forward_ex(h, None, n) == -1
+    io = RolloutIO()
+    io.bs, io.nsteps, io.frame_stride, io.dt = 2, 65, 32, 5e-4
+    assert lib.ppr_rollout_forward_ex(h, C.byref(io), n) == -1                         # missing pointers
+    for f in ("q_init", "qd_init", "refs", "target_ke", "target_kd", "body_inv_mass", "body_inertia", "body_inv_inertia",
+              "out_pos", "out_vel", "workspace"):
+        setattr(io, f, x.data_ptr())
+    io.workspace_bytes = 16
+    assert lib.ppr_rollout_forward_ex(h, C.byref(io), n) == -4                         # workspace too small
+    io.loss_pos = x.data_ptr()
+    assert lib.ppr_rollout_forward_ex(h, C.byref(io), n) == -1                         # loss requested without targets
+    io.loss_pos = None
+    io.workspace_bytes = lib.ppr_rollout_workspace_bytes(h, 2, 65)
+    assert lib.ppr_rollout_backward_ex(h, C.byref(io), n) == -1                        # no adjoint outputs / nothing to seed
+    io.bs = 0
+    assert lib.ppr_rollout_forward_ex(h, C.byref(io), n) == 0                          # empty batch
+    assert lib.ppr_rollout_shared_grad_floats(h) == 2 * env.nqd + 19 * env.nb
+    assert lib.ppr_refs_from_frames(65, 32, 0, 4, p, p, n) == -1 and lib.ppr_refs_from_frames(0, 32, 3, 4, p, p, n) == 0
+    assert lib.ppr_model_set_ground(C.c_void_p(None), 1) == -3
+
+
+def test_ground_flag_skips_the_contact_kernel():
+    """``env.ground = False``: compute_forces skips eval_body_contacts and grf stays at res_f (integrator_euler.py:492-510)."""
+    from ppr_diffphys_b200 import SimEnv
+    stride, F, bs = 8, 3, 3
+    T = stride * (F - 1) + 1
+    rm, d = make_inputs("human", bs=bs, T=T, seed=2)
+    d = settle_height(rm, d, 0.003)
+    dev = torch.device("cuda:0")
+    out = {}
+    for ground in (True, False):
+        env = SimEnv(rm)
+        env.ground = ground
+        a, _, _ = flat_args(d, dev, drop=("torques", "res_f"))
+        pos, vel, caller = run_cuda(env, a, bs, T, stride)
+        (pos.sum() + vel.sum()).backward()
+        assert all(torch.isfinite(a[k].grad).all() for k in a if a[k] is not None and a[k].grad is not None)
+        out[ground] = (pos.detach(), torch.stack(caller.grfs))
+    assert float(out[True][1].abs().max()) > 1.0            # in contact
+    assert float(out[False][1].abs().max()) == 0.0          # no ground: grf = res_f = 0
+    assert float((out[True][0] - out[False][0]).abs().max()) > 1e-5
 
 
 def test_joint_X_p_setter_changes_fk():
