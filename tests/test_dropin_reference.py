@@ -65,6 +65,17 @@ def test_reference_phys_model_trains_on_the_operator_interface(tmp_path, monkeyp
     last = sum(l["loss_traj"] for l in losses[-5:]) / 5
     print("loss_traj first5 %.5f last5 %.5f" % (first, last))
     assert last < first
+    # the evaluation pass of main.py:77-79: ONE env over the whole clip (39 frames = 1 255 substeps), no noise
+    model.eval()
+    model.reinit_envs(1, frames_per_wdw=model.total_frames, is_eval=True)
+    with torch.no_grad():
+        ev = model.forward()
+    assert len(model.steps_idx) == 33 * 38 + 1 and len(model.sim_trajs) == model.total_frames == 39
+    assert set(ev) == LOSS_KEYS and all(torch.isfinite(v) for v in ev.values())
+    # back to the (cached) training envs, like the next line of main.py
+    model.train()
+    model.reinit_envs(10, frames_per_wdw=24, is_eval=False)
+    assert model.num_envs == 10 and len(model.steps_idx) == 760
 
 
 @needs_ref
