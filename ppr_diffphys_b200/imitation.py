@@ -187,8 +187,10 @@ class ImitationModel(nn.Module):
         self.progress = 0.0
         explicit = [self.global_q, self.target_ke, self.target_kd, self.body_mass]
         nets = [p for m in (self.root_pose_mlp, self.joint_angle_mlp, self.vel_mlp) for p in m.parameters()]
+        # fused=True: one multi-tensor kernel per parameter group instead of ~10 foreach launches (the step stays outside
+        # the captured graph: its skip / roll-back decision needs the gradient norm on the host, as in the reference)
         self.optimizer = torch.optim.AdamW([{"params": explicit, "lr": lr * 10}, {"params": nets, "lr": lr}],
-                                           weight_decay=1e-4)
+                                           weight_decay=1e-4, fused=self.device.type == "cuda")
         total = max(2, total_iters)
         self.scheduler = torch.optim.lr_scheduler.OneCycleLR(self.optimizer, [lr * 10, lr], total, pct_start=2.0 / total,
                                                              cycle_momentum=False, anneal_strategy="linear",
