@@ -8,8 +8,8 @@ method names and data flow for the part that feeds and consumes the simulator bo
 
 and the same learnable quantities (control-reference networks, PD gains, body mass, global SE(3), initial velocity).
 What is deliberately NOT mirrored (out of the hot-path scope): visualiser / ``query()`` mesh
-articulation, lab4d coupling, per-parameter median gradient clipping, checkpoint files on disk (the in-memory
-queue and its roll-back are mirrored: save_checkpoint / update).
+articulation, lab4d coupling, checkpoint files on disk (the in-memory queue and its roll-back are mirrored:
+save_checkpoint / update, and so is the per-parameter median gradient clipping: median_clip_).
 Differences that matter for speed: mocap interpolation runs in torch on the device (the reference calls scipy on
 the CPU every step, :605-609); shared parameters are passed UN-replicated to ``ForwardWarp`` (the reference
 replicates + inverts bs*nb 3x3 matrices per step, :723-730).
@@ -96,6 +96,36 @@ def reduce_loss(loss_seq, clip=False):
         loss_seq = torch.where(cut, torch.zeros_like(loss_seq), loss_seq)
     pos = loss_seq > 0
     return torch.where(pos, loss_seq, torch.zeros_like(loss_seq)).sum() / pos.sum().clamp_min(1)
+
+
+def median_clip_(named_grads, queue, queue_length=10, scale=5.0, norms=None):
+    """Per-parameter outlier clipping of dp_model.py:965-998: every parameter keeps a queue of its recent gradient norms;
+    once the queue holds more than ``queue_length`` entries, a gradient whose norm exceeds ``scale`` x the median of the
+    queue (without its newest entry) is scaled down to that median and NOT enqueued, any other norm replaces the oldest
+    entry.  ``named_grads``: iterable of (name, grad tensor); ``queue``: dict name -> list of floats, updated in place.
+    All norms come to the host in ONE read (or are passed in as ``norms``, one float per non-None gradient).
+    Returns {name: (norm, median or None, clipped)}."""
+    named_grads = [(n, g) for n, g in named_grads if g is not None]
+    if not named_grads:
+        return {}
+    if norms is None:
+        norms = torch.stack(torch._foreach_norm([g for _, g in named_grads])).tolist()   # one multi-tensor launch, one read
+    out = {}
+    for (name, g), norm in zip(named_grads, norms):
+        q = queue.setdefault(name, [])
+        med, clipped = None, False
+        if len(q) > queue_length:
+            med = float(torch.tensor(q[:-1]).median())
+            if norm > scale * med:
+                g.mul_(med / (norm + 1e-6))                  # clip_grad_norm_(p, med_grad)
+                clipped = True
+            else:
+                q.append(norm)
+                q.pop(0)
+        else:
+            q.append(norm)
+        out[name] = (norm, med, clipped)
+    return out
 
 
 def rotate_frame(global_q, q):
@@ -356,9 +386,13 @@ class ImitationModel(nn.Module):
         a no-op) and the model / optimizer / scheduler roll back to the snapshot of two rounds ago when there is one
         (:947-952).  ``keep_grads``: leave the .grad tensors in place (GraphedStep re-fills the same memory on the
         next replay)."""
-        params = [p for g in self.optimizer.param_groups for p in g["params"] if p.grad is not None]
-        grad_norm = torch.nn.utils.clip_grad_norm_(params, thresh)
-        skipped = bool(not torch.isfinite(grad_norm) or grad_norm > thresh)
+        named = [(n, p) for n, p in self.named_parameters() if p.grad is not None]
+        # every per-parameter norm and the total in ONE multi-tensor launch + ONE host read (clip_grad_norm_(params, thresh)
+        # would only rescale when the total exceeds ``thresh`` -- and then the iteration is dropped anyway)
+        norms_t = torch.stack(torch._foreach_norm([p.grad for _, p in named]))
+        vals = torch.cat([norms_t, norms_t.norm(2)[None]]).tolist()
+        grad_norm = vals[-1]
+        skipped = bool(not math.isfinite(grad_norm) or grad_norm > thresh)
         if skipped and getattr(self, "_cache", [None])[0] is not None:
             sd, od, sch = self._cache[0]
             with torch.no_grad():                            # in place: parameter storage (and a captured graph) stay valid
@@ -367,6 +401,9 @@ class ImitationModel(nn.Module):
             self.optimizer.load_state_dict(od)
             self.scheduler.load_state_dict(sch)
         if not skipped:
+            if not hasattr(self, "_grad_queue"):
+                self._grad_queue = {}
+            median_clip_([(n, p.grad) for n, p in named], self._grad_queue, norms=vals[:-1])    # dp_model.py:965-998
             self.optimizer.step()
         self.scheduler.step()
         if not keep_grads:

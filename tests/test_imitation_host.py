@@ -232,3 +232,39 @@ def test_reduce_loss_clipping_matches_the_reference_loop():
         assert torch.allclose(reduce_loss(x), x[x > 0].mean())
     z = torch.zeros(3, 4)
     assert float(reduce_loss(z, clip=True)) == 0.0 and float(reduce_loss(z)) == 0.0
+
+
+def test_median_gradient_clipping_matches_the_reference_queue():
+    """median_clip_ == the per-parameter queue logic of dp_model.py:965-998 (literal re-statement with
+    torch.nn.utils.clip_grad_norm_), over a sequence of gradients with outliers."""
+    from ppr_diffphys_b200.imitation import median_clip_
+    g = torch.Generator().manual_seed(0)
+    names = ["a", "b"]
+    mine_q, ref_q = {}, {}
+    for it in range(40):
+        grads = {n: torch.randn(7, generator=g) * (1.0 if n == "a" else 0.1) for n in names}
+        if it in (15, 16, 30):
+            grads["a"] = grads["a"] * 50.0                       # outliers
+        ref = {}
+        for n in names:                                          # the reference's loop
+            p = torch.nn.Parameter(torch.zeros(7))
+            p.grad = grads[n].clone()
+            grad = p.grad.reshape(-1).norm(2, -1)
+            q = ref_q.setdefault(n, [])
+            if len(q) > 10:
+                med = torch.stack(q[:-1]).median()
+                if grad > 5.0 * med:
+                    torch.nn.utils.clip_grad_norm_(p, med)
+                else:
+                    q.append(grad)
+                    q.pop(0)
+            else:
+                q.append(grad)
+            ref[n] = p.grad
+        mine = {n: grads[n].clone() for n in names}
+        info = median_clip_(mine.items(), mine_q)
+        for n in names:
+            assert torch.allclose(mine[n], ref[n], rtol=1e-5, atol=1e-7), (it, n)
+            assert len(mine_q[n]) == len(ref_q[n]) and all(abs(x - float(y)) < 1e-5 * max(1.0, x) for x, y in zip(mine_q[n], ref_q[n]))
+        if it in (15, 16, 30):
+            assert info["a"][2] and not info["b"][2]
