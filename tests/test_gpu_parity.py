@@ -486,6 +486,30 @@ def test_c_abi_error_codes(monkeypatch):
     assert lib.ppr_model_set_ground(C.c_void_p(None), 1) == -3
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_models_on_two_devices_in_one_process():
+    """The > 48 kB dynamic shared-memory opt-in of the rollout kernels is per DEVICE, and the library must launch on the
+    model's device whatever the caller's current device is: same rollout + adjoint on cuda:0 and cuda:1, bit-identical."""
+    from ppr_diffphys_b200 import SimEnv
+    stride, F, bs = 8, 3, 9
+    T = stride * (F - 1) + 1
+    rm, d = make_inputs("human", bs=bs, T=T, seed=7)
+    d = settle_height(rm, d, 0.002)
+    out = []
+    for dev_id in (0, 1):
+        dev = torch.device("cuda", dev_id)
+        env = SimEnv(rm, device=dev)
+        torch.cuda.set_device(0)                    # the caller's current device stays 0 for both
+        a, _, _ = flat_args(d, dev)
+        pos, vel, _ = run_cuda(env, a, bs, T, stride)
+        ((pos ** 2).sum() + (vel ** 2).sum() * 0.01).backward()
+        torch.cuda.synchronize(dev)
+        out.append((pos.detach().cpu(), [a[k].grad.cpu() for k in KEYS]))
+    assert torch.equal(out[0][0], out[1][0])
+    for x, y in zip(out[0][1], out[1][1]):
+        assert torch.equal(x, y)
+
+
 def test_ground_flag_skips_the_contact_kernel():
     """``env.ground = False``: compute_forces skips eval_body_contacts and grf stays at res_f (integrator_euler.py:492-510)."""
     from ppr_diffphys_b200 import SimEnv
