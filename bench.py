@@ -180,6 +180,53 @@ def kernel_source_hash():
     return h.hexdigest()[:16]
 
 
+def step_functions():
+    """The caller-side glue of the bench step as two autograd Functions with hand-written backwards: the same values and
+    gradients as the plain torch expressions in their docstrings (tests/test_bench_host.py compares them), in a third of
+    the device ops -- at the small configs the step is launch-bound and every elementwise op is a graph node."""
+    import torch
+
+    class StepLoss(torch.autograd.Function):
+        """(pos[-1,:,:3] - pos[0,:,:3]).pow(2).mean() + 1e-3 * vel[-1].pow(2).mean()"""
+
+        @staticmethod
+        def forward(ctx, pos, vel):
+            d = pos[-1, :, :3] - pos[0, :, :3]
+            v = vel[-1]
+            ctx.save_for_backward(d, v)
+            ctx.shapes = (pos.shape, vel.shape)
+            return torch.add(torch.dot(d.reshape(-1), d.reshape(-1)) / d.numel(),
+                             torch.dot(v.reshape(-1), v.reshape(-1)), alpha=1e-3 / v.numel())
+
+        @staticmethod
+        def backward(ctx, g):
+            d, v = ctx.saved_tensors
+            gpos = torch.zeros(ctx.shapes[0], device=d.device, dtype=d.dtype)
+            gvel = torch.zeros(ctx.shapes[1], device=d.device, dtype=d.dtype)
+            gd = d * (g * (2.0 / d.numel()))
+            gpos[-1, :, :3] = gd
+            torch.neg(gd, out=gpos[0, :, :3]) if gpos.shape[0] > 1 else gpos[0, :, :3].zero_()
+            torch.mul(v, g * (2e-3 / v.numel()), out=gvel[-1])
+            return gpos, gvel
+
+    class MassChain(torch.autograd.Function):
+        """(1 / m, nI * m[:, None, None], nI_inv / m[:, None, None]): what dp_model.py:726-730 derives from body_mass"""
+
+        @staticmethod
+        def forward(ctx, m, nI, nI_inv):
+            inv_m = 1.0 / m
+            ctx.save_for_backward(inv_m, nI, nI_inv)
+            return inv_m, nI * m[:, None, None], nI_inv * inv_m[:, None, None]
+
+        @staticmethod
+        def backward(ctx, g_inv_m, g_I, g_inv_I):
+            inv_m, nI, nI_inv = ctx.saved_tensors
+            a = (g_inv_I * nI_inv).sum((1, 2)).add_(g_inv_m)         # d/d(1/m)
+            return torch.addcmul((g_I * nI).sum((1, 2)), a, inv_m * inv_m, value=-1.0), None, None
+
+    return StepLoss, MassChain
+
+
 def workload_batch(env, w, bs, nsteps, seed, pinned_host=False):
     """The synthetic inputs of a bench workload -- also what tests/test_gpu_bench_parity.py checks against the oracle."""
     from ppr_diffphys_b200.synth import make_batch
@@ -225,6 +272,7 @@ def run_gpu_arm(args):
     p_kd = torch.as_tensor(rm.joint_target_kd, device=dev).clone().requires_grad_(True)
     p_mass = torch.as_tensor(rm.body_mass, device=dev).clone().requires_grad_(True)
     NP = 2 * nqd + nb + 1                         # shared-parameter gradients + the loss: one D2H read / one all-reduce
+    StepLoss, MassChain = step_functions()
 
     def step(inp, replicate=False, zero_forces=False):
         """one optimisation step of the hot path on device-resident inputs -> packed [grad ke | grad kd | grad mass | loss]"""
@@ -235,13 +283,12 @@ def run_gpu_arm(args):
             ke, kd, mass, inv_m, I, inv_I = shared_param_chain(p_ke, p_kd, p_mass, nI, bs)
         else:           # un-replicated parameters: the kernels read one shared copy, gradients are reduced on the device
             ke, kd, mass = p_ke, p_kd, p_mass
-            inv_m, I = 1.0 / p_mass, nI * p_mass[:, None, None]
-            inv_I = nI_inv * inv_m[:, None, None]       # inverse(nI * m) = inverse(nI) / m
+            inv_m, I, inv_I = MassChain.apply(p_mass, nI, nI_inv)   # inverse(nI * m) = inverse(nI) / m
         torques = res_f = None
         if zero_forces:  # exact zeros passed as real tensors, as the reference does (dp_model.py:529,536)
             torques, res_f = inp["torques0"], inp["res_f0"]
         pos, vel = ForwardWarp.apply(q_init, qd_init, torques, res_f, refs, ke, kd, mass, inv_m, I, inv_I, caller)
-        loss = (pos[-1, :, :3] - pos[0, :, :3]).pow(2).mean() + 1e-3 * vel[-1].pow(2).mean()
+        loss = StepLoss.apply(pos, vel)
         # every gradient the reference's backward returns: shared parameters (.grad of the three leaves) + per-env control
         # references / initial state (.grad of the per-step leaves)
         for p in (p_ke, p_kd, p_mass):
@@ -324,6 +371,15 @@ def run_gpu_arm(args):
     for _ in range(2):   # (the first eager steps after the capture re-grow the allocator's ordinary pool)
         eager_step()
     ms_eager = timed(eager_step, max(3, args.steps // 4)) / max(3, args.steps // 4)
+    if args.census and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(static)
+            torch.cuda.synchronize()
+        rows = sorted(prof.key_averages(), key=lambda r: -r.count)
+        print("kernel census of one step: %d device ops" % sum(r.count for r in rows), file=sys.stderr)
+        for r in rows:
+            print("  %3d x %8.1f us  %s" % (r.count, r.device_time_total / max(r.count, 1), r.key[:110]), file=sys.stderr)
     # ---- kernel-only timing with CUDA events on the launching stream (roofline)
     ke = p_ke.detach()[None].expand(bs, nqd).reshape(-1).contiguous()
     kd = p_kd.detach()[None].expand(bs, nqd).reshape(-1).contiguous()
@@ -564,6 +620,8 @@ def main():
                     help="also time the reference's literal convention (replicated parameters, real zero torques/res_f) "
                          "even with --no-extras")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of one CUDA-graph replay")
+    ap.add_argument("--census", action="store_true",
+                    help="print the kernel census of one step (torch.profiler, outside every timed region) to stderr")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --envs per GPU (default); strong: --total-envs sharded over the ranks")
     ap.add_argument("--total-envs", type=int, default=0, help="total envs of a strong-scaling run (default: workload size)")

@@ -44,3 +44,32 @@ def test_traffic_file_is_stamped_with_a_kernel_source_hash():
         assert tj[wl]["rollout_forward_kernel"] > 0 and tj[wl]["rollout_backward_kernel"] > 0
     if tj["kernel_source_hash"] != h:    # not an error: bench.py then reports traffic = null with a note
         print("profiles/traffic.json is stale for the current kernel sources (%s vs %s)" % (tj["kernel_source_hash"], h))
+
+
+def test_step_functions_equal_the_plain_torch_expressions():
+    """bench.py's hand-written StepLoss / MassChain: same value and gradients as the composed expressions."""
+    StepLoss, MassChain = bench.step_functions()
+    g = torch.Generator().manual_seed(1)
+    for F in (1, 3):
+        pos = torch.randn(F, 26, 7, generator=g, dtype=torch.float64).requires_grad_(True)
+        vel = torch.randn(F, 26, 6, generator=g, dtype=torch.float64).requires_grad_(True)
+        ref = (pos[-1, :, :3] - pos[0, :, :3]).pow(2).mean() + 1e-3 * vel[-1].pow(2).mean()
+        gr = torch.autograd.grad(ref * 1.7, (pos, vel))
+        out = StepLoss.apply(pos, vel)
+        go = torch.autograd.grad(out * 1.7, (pos, vel))
+        assert torch.allclose(out, ref, rtol=1e-12, atol=1e-14)
+        for a, b in zip(go, gr):
+            assert torch.allclose(a, b, rtol=1e-12, atol=1e-14)
+    m = (torch.rand(13, generator=g, dtype=torch.float64) + 0.5).requires_grad_(True)
+    nI = torch.randn(13, 3, 3, generator=g, dtype=torch.float64)
+    nI = nI @ nI.transpose(1, 2) + torch.eye(3, dtype=torch.float64)
+    nI_inv = torch.linalg.inv(nI)
+    w = [torch.randn(13, generator=g, dtype=torch.float64), torch.randn(13, 3, 3, generator=g, dtype=torch.float64),
+         torch.randn(13, 3, 3, generator=g, dtype=torch.float64)]
+    ref = (1.0 / m, nI * m[:, None, None], torch.linalg.inv(nI * m[:, None, None]))
+    out = MassChain.apply(m, nI, nI_inv)
+    for a, b in zip(out, ref):
+        assert torch.allclose(a, b, rtol=1e-10, atol=1e-12)
+    gr, = torch.autograd.grad(sum((a * b).sum() for a, b in zip(ref, w)), m)
+    go, = torch.autograd.grad(sum((a * b).sum() for a, b in zip(out, w)), m)
+    assert torch.allclose(go, gr, rtol=1e-9, atol=1e-12)
