@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--log-every", type=int, default=10)
     ap.add_argument("--lr", type=float, default=1e-4)
     ap.add_argument("--no-graph", action="store_true", help="eager iterations instead of one CUDA-graph replay each")
+    ap.add_argument("--eager-update", action="store_true",
+                    help="capture forward + backward only; gradient norms, clipping and AdamW run eagerly after each replay")
     args = ap.parse_args()
     torch.manual_seed(8)
     model = ImitationModel(args.robot, args.seqname, total_iters=args.iters, lr=args.lr)
@@ -37,7 +39,7 @@ def main():
     model.reinit_envs(args.num_envs, args.frames_per_wdw)
     T = len(model.steps_idx)
     losses, times = [], []
-    step = None if args.no_graph else GraphedStep(model)
+    step = None if args.no_graph else GraphedStep(model, capture_update=not args.eager_update)
     for it in range(args.iters):
         model.progress = it / max(1, args.iters - 1)
         if it % 20 == 0:

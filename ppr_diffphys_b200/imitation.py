@@ -128,6 +128,28 @@ def median_clip_(named_grads, queue, queue_length=10, scale=5.0, norms=None):
     return out
 
 
+def median_clip_device_(grads, queue, count, skip, queue_length=10, scale=5.0, norms=None):
+    """``median_clip_`` as tensor operations only -- no host read, CUDA-graph capturable.  ``queue``: [n, queue_length+1]
+    tensor of recent norms per gradient, oldest first; ``count``: 0-dim long tensor, entries held (all gradients enqueue in
+    lock step until the queue is full); ``skip``: 0-dim bool tensor, True = the whole iteration is dropped (nothing is
+    clipped or enqueued).  Scales the clipped gradients in place, updates ``queue`` / ``count`` in place and returns
+    (norms [n], clipped [n] bool)."""
+    n, L = len(grads), queue_length
+    if norms is None:
+        norms = torch.stack(torch._foreach_norm(grads))
+    full = count > L
+    med = queue[:, :L].median(dim=1).values              # lower median, like torch.tensor(q[:-1]).median()
+    clipped = full & (norms > scale * med) & ~skip
+    factor = torch.where(clipped, med / (norms + 1e-6), torch.ones_like(norms))
+    torch._foreach_mul_(grads, list(factor.unbind()))
+    enqueue = ~skip & ~clipped
+    shifted = torch.cat([queue[:, 1:], norms[:, None]], 1)                       # full: drop the oldest
+    filled = queue.scatter(1, count.clamp(max=L).reshape(1, 1).expand(n, 1), norms[:, None])
+    queue.copy_(torch.where(enqueue[:, None], torch.where(full, shifted, filled), queue))
+    count.add_((~skip & ~full).to(count.dtype))
+    return norms, clipped
+
+
 def rotate_frame(global_q, q):
     """T = T_global @ T  (dp_utils.py:60-72) on (...,7) poses."""
     R = quat_to_matrix(global_q[3:7])
@@ -217,10 +239,13 @@ class ImitationModel(nn.Module):
         self.progress = 0.0
         explicit = [self.global_q, self.target_ke, self.target_kd, self.body_mass]
         nets = [p for m in (self.root_pose_mlp, self.joint_angle_mlp, self.vel_mlp) for p in m.parameters()]
-        # fused=True: one multi-tensor kernel per parameter group instead of ~10 foreach launches (the step stays outside
-        # the captured graph: its skip / roll-back decision needs the gradient norm on the host, as in the reference)
-        self.optimizer = torch.optim.AdamW([{"params": explicit, "lr": lr * 10}, {"params": nets, "lr": lr}],
-                                           weight_decay=1e-4, fused=self.device.type == "cuda")
+        # fused=True: one multi-tensor kernel per parameter group instead of ~10 foreach launches.  On CUDA the step is
+        # capturable (learning rates live in device tensors the scheduler fills in place; a dropped iteration is the
+        # optimizer's device-side ``found_inf`` flag), so that GraphedStep can replay it with the rest of the iteration
+        cuda = self.device.type == "cuda"
+        as_lr = (lambda v: torch.tensor(v, device=self.device)) if cuda else (lambda v: v)
+        self.optimizer = torch.optim.AdamW([{"params": explicit, "lr": as_lr(lr * 10)}, {"params": nets, "lr": as_lr(lr)}],
+                                           weight_decay=1e-4, fused=True, capturable=cuda)
         total = max(2, total_iters)
         self.scheduler = torch.optim.lr_scheduler.OneCycleLR(self.optimizer, [lr * 10, lr], total, pct_start=2.0 / total,
                                                              cycle_momentum=False, anneal_strategy="linear",
@@ -280,10 +305,11 @@ class ImitationModel(nn.Module):
     def compute_frame_start(self):
         return self.compute_frame_start_host().to(self.device)
 
-    def fk_pos_vel(self, q, ja, qd, jad):
-        """(bs,F,..) targets -> body poses / twists through ForwardKinematics (dp_model.py:588-603)."""
+    def fk_pos_vel(self, q, ja, qd=None, jad=None):
+        """(bs,F,..) targets -> body poses / twists through ForwardKinematics (dp_model.py:588-603).  ``qd`` None: poses
+        only (the twists come back zero)."""
         tq = torch.cat([q, ja], -1).permute(1, 0, 2).contiguous()
-        tqd = convert_ppr_warp(torch.cat([qd, jad], -1).permute(1, 0, 2).contiguous())
+        tqd = None if qd is None else convert_ppr_warp(torch.cat([qd, jad], -1).permute(1, 0, 2).contiguous())
         bq, bqd, frames = ForwardKinematics.apply(tq, tqd, self.env)
         return bq, convert_ppr_warp(bqd), frames
 
@@ -294,11 +320,10 @@ class ImitationModel(nn.Module):
         delta_root = self.root_pose_mlp(fid).view(bs, T, 6)
         # rotate_frame(global_q, .) then compose_delta(., delta_root): one fused kernel each way (ops.FrameCompose)
         target_q, queried_q = FrameCompose.apply(self.global_q, torch.cat([msm["pos"], msm["orn"]], -1), delta_root)
-        # the target twists only feed the (unused) twist output of the target FK: no gradient path, none recorded
-        target_qd = rotate_frame_vel(self.global_q.detach(), torch.cat([msm["vel"], msm["avel"]], -1))  # bs,T,6
+        # the reference also rotates the mocap twists into the target FK (rotate_frame_vel, dp_model.py:626-636), whose
+        # twist OUTPUT (target_velocity) nothing reads: not computed here
         f2s = slice(0, None, self.steps_per_fr_interval)   # == self.frame2step (evenly strided), as a view: no index tensor
-        target_position, _, self.target_trajs = self.fk_pos_vel(target_q[:, f2s], msm["jang"][:, f2s],
-                                                                target_qd[:, f2s], msm["jvel"][:, f2s])
+        target_position, _, self.target_trajs = self.fk_pos_vel(target_q[:, f2s], msm["jang"][:, f2s])
         delta_ja = self.joint_angle_mlp(fid).view(bs, T, -1)
         queried_qd = self.vel_mlp(fid).view(bs, T, -1)
         queried_ja = msm["jang"] + delta_ja
@@ -380,46 +405,73 @@ class ImitationModel(nn.Module):
         self._cache[1] = (deepcopy(self.state_dict()), deepcopy(self.optimizer.state_dict()),
                           deepcopy(self.scheduler.state_dict()))
 
-    def update(self, thresh=10.0, keep_grads=False):
-        """clip, sanity-check and apply the gradients (dp_model.py:511-548,936-963): an iteration whose gradient norm
-        is non-finite or above ``thresh`` is skipped (the reference drops the gradients, which makes its optimizer step
-        a no-op) and the model / optimizer / scheduler roll back to the snapshot of two rounds ago when there is one
-        (:947-952).  ``keep_grads``: leave the .grad tensors in place (GraphedStep re-fills the same memory on the
-        next replay)."""
+    def update_device(self, thresh=10.0):
+        """The device part of ``update``: gradient norms, the drop decision, per-parameter median clipping and the AdamW
+        step as tensor operations with NO host read (CUDA-graph capturable).  ``thresh``: float or 0-dim tensor.  A
+        dropped iteration (norm non-finite or above ``thresh``) is the optimizer's ``found_inf`` flag: the fused AdamW
+        kernel leaves parameters, moments and step counts untouched.  Leaves [grad_norm, dropped] in ``self._upd_info``."""
         named = [(n, p) for n, p in self.named_parameters() if p.grad is not None]
-        # every per-parameter norm and the total in ONE multi-tensor launch + ONE host read (clip_grad_norm_(params, thresh)
-        # would only rescale when the total exceeds ``thresh`` -- and then the iteration is dropped anyway)
-        norms_t = torch.stack(torch._foreach_norm([p.grad for _, p in named]))
-        vals = torch.cat([norms_t, norms_t.norm(2)[None]]).tolist()
-        grad_norm = vals[-1]
-        skipped = bool(not math.isfinite(grad_norm) or grad_norm > thresh)
+        grads = [p.grad for _, p in named]
+        if not hasattr(self, "_clip_queue"):
+            dev = grads[0].device
+            self._clip_names = [n for n, _ in named]
+            self._clip_queue = torch.zeros(len(named), 11, device=dev)
+            self._clip_count = torch.zeros((), dtype=torch.long, device=dev)
+            self._upd_info = torch.zeros(2, device=dev)
+            self.optimizer.found_inf = torch.zeros((), device=dev)
+        assert [n for n, _ in named] == self._clip_names, "the set of parameters with gradients changed"
+        norms = torch.stack(torch._foreach_norm(grads))       # every per-parameter norm in one multi-tensor launch
+        total = norms.norm(2)
+        skip = ~(total <= thresh)                             # NaN / inf / above the threshold (dp_model.py:941-946)
+        median_clip_device_(grads, self._clip_queue, self._clip_count, skip, norms=norms)   # dp_model.py:965-998
+        self.optimizer.found_inf.copy_(skip)
+        self.optimizer.step()
+        self._upd_info.copy_(torch.stack([total, skip.to(total.dtype)]))
+
+    def finish_update(self, keep_grads=False):
+        """The host part of ``update``: ONE read of [grad_norm, dropped]; a dropped iteration rolls the model and the
+        optimizer back IN PLACE (parameter / moment storage, and with it a captured graph, stays valid) to the snapshot
+        of two rounds ago when there is one (dp_model.py:947-952); the scheduler steps either way."""
+        from copy import deepcopy
+        grad_norm, skipped = self._upd_info.tolist()
+        skipped = bool(skipped)
         if skipped and getattr(self, "_cache", [None])[0] is not None:
             sd, od, sch = self._cache[0]
-            with torch.no_grad():                            # in place: parameter storage (and a captured graph) stay valid
+            with torch.no_grad():
                 for k, v in self.state_dict().items():
                     v.copy_(sd[k])
-            self.optimizer.load_state_dict(od)
-            self.scheduler.load_state_dict(sch)
-        if not skipped:
-            if not hasattr(self, "_grad_queue"):
-                self._grad_queue = {}
-            median_clip_([(n, p.grad) for n, p in named], self._grad_queue, norms=vals[:-1])    # dp_model.py:965-998
-            self.optimizer.step()
+                params = [p for g in self.optimizer.param_groups for p in g["params"]]
+                for i, p in enumerate(params):
+                    for k, v in self.optimizer.state.get(p, {}).items():
+                        saved = od["state"].get(i, {}).get(k)
+                        v.zero_() if saved is None else v.copy_(saved)   # (snapshot older than the first step: zeros)
+            self.scheduler.load_state_dict(deepcopy(sch))    # (the learning-rate tensors are re-filled by scheduler.step() below)
         self.scheduler.step()
         if not keep_grads:
             self.optimizer.zero_grad()
         return {"grad_norm": float(grad_norm), "skipped": skipped}
 
+    def update(self, thresh=10.0, keep_grads=False):
+        """clip, sanity-check and apply the gradients (dp_model.py:511-548,936-963): an iteration whose gradient norm
+        is non-finite or above ``thresh`` is skipped (the reference drops the gradients, which makes its optimizer step
+        a no-op) and the model / optimizer / scheduler roll back to the snapshot of two rounds ago when there is one
+        (:947-952).  ``keep_grads``: leave the .grad tensors in place."""
+        self.update_device(thresh)
+        return self.finish_update(keep_grads)
+
 
 class GraphedStep:
-    """forward + losses + backward of one optimisation iteration captured ONCE in a CUDA graph and replayed.
+    """One whole optimisation iteration -- forward, losses, backward, gradient norms, drop decision, median clipping and
+    the AdamW step -- captured ONCE in a CUDA graph and replayed.
 
     The reference-shaped problem (10..64 windows x 760 substeps, dp_model.py:354-367) cannot fill a B200: an iteration
     is a few hundred small launches (three MLPs, mocap interpolation, two FK calls, the rollout pair, se3 losses
-    and their backward) whose launch overhead, not their run time, sets the iteration time.  Everything that
-    changes between iterations enters through two static device buffers (window start frames, initial-state
-    noise), both drawn on the host exactly like the eager path, so the two paths consume the same random stream.
-    The optimizer step stays eager: its skip decision needs the gradient norm on the host (as in the reference).
+    and their backward, the optimizer) whose launch overhead, not their run time, sets the iteration time.  Everything
+    that changes between iterations enters through static device buffers (window start frames, initial-state noise, the
+    drop threshold, the learning rates), the first two drawn on the host exactly like the eager path, so the two paths
+    consume the same random stream.  The host reads two floats per iteration (gradient norm, dropped flag) and keeps the
+    rare roll-back and the scheduler (``ImitationModel.finish_update``).  ``capture_update=False`` captures forward +
+    backward only and runs ``update()`` eagerly.
 
     Limitation: the kernel arguments are baked into the captured graph BY VALUE, including the model scalars (attach
     gains, gravity, ground flag, checkpoint policy) and the joint_X_p pointer -- ``env.set_attach / set_gravity /
@@ -432,27 +484,35 @@ class GraphedStep:
             out, info = step()              # out: dict of static loss tensors, info: update() result
     """
 
-    def __init__(self, model, warmup=3):
+    def __init__(self, model, warmup=3, capture_update=True):
         self.model = m = model
         dev = m.device
+        self.capture_update = bool(capture_update)
         self._snap = m.env._snapshot()[:-1]      # (the tensor version legitimately changes under in-place updates)
         self.frame_start = torch.zeros(m.num_envs, device=dev)
         self.noise = torch.zeros(m.num_envs, m.env.nq, device=dev)
+        self.thresh = torch.full((), -1.0, device=dev)   # -1: every warm-up iteration is "dropped" -> nothing changes
+        self._thresh_host = -1.0
         self._h_frame_start = torch.zeros(m.num_envs).pin_memory()
         self._h_noise = torch.zeros(m.num_envs, m.env.nq).pin_memory()
         m.optimizer.zero_grad(set_to_none=True)
+
+        def iteration():
+            out = m(frame_start=self.frame_start, noise=self.noise)
+            out["total_loss"].backward()
+            if self.capture_update:
+                m.update_device(self.thresh)
+            return out
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):       # warm-up off the default stream (allocator pools, lazy kernel attributes)
-            for _ in range(warmup):
-                out = m(frame_start=self.frame_start, noise=self.noise)
-                out["total_loss"].backward()
+        with torch.cuda.stream(side):       # warm-up off the default stream (allocator pools, lazy kernel attributes,
+            for _ in range(warmup):         # the optimizer's lazily created moments)
+                iteration()
                 m.optimizer.zero_grad(set_to_none=True)
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = m(frame_start=self.frame_start, noise=self.noise)
-            self.out["total_loss"].backward()
+            self.out = iteration()
         self.launches_per_replay = None
 
     def __call__(self, frame_start=None, thresh=10.0):
@@ -470,6 +530,10 @@ class GraphedStep:
         else:
             self._h_noise.copy_(noise)
             self.noise.copy_(self._h_noise, non_blocking=True)
+        if self.capture_update and float(thresh) != self._thresh_host:
+            self._thresh_host = float(thresh)
+            self.thresh.fill_(self._thresh_host)
         self.graph.replay()
-        info = m.update(thresh, keep_grads=True)
-        return self.out, info
+        if self.capture_update:
+            return self.out, m.finish_update(keep_grads=True)
+        return self.out, m.update(thresh, keep_grads=True)

@@ -50,35 +50,43 @@ def test_eval_rollout_side_channels():
 
 
 def test_graphed_step_matches_eager_iterations():
-    """One CUDA-graph replay per iteration (GraphedStep) == the eager forward / backward / update sequence: same
-    random stream, same losses and the same parameters after a few iterations."""
+    """One CUDA-graph replay per iteration (GraphedStep; with the update captured too, or run eagerly after the replay)
+    == the eager forward / backward / update sequence: same random stream, same losses and the same parameters after a
+    few iterations -- including an iteration dropped by the gradient-norm threshold, which must change nothing."""
     from ppr_diffphys_b200.imitation import GraphedStep, ImitationModel
 
-    def run(graphed, iters=6):
+    def run(graphed, capture_update=True, iters=7, drop_at=3):
         torch.manual_seed(8)
         model = ImitationModel("laikago", "mi-trot", total_iters=iters, lr=1e-4, seed=3)
         model.record_forces = False
         model.train()
         model.reinit_envs(6, 5)
-        step = GraphedStep(model) if graphed else None
+        step = GraphedStep(model, capture_update=capture_update) if graphed else None
         losses = []
         for it in range(iters):
             model.progress = it / iters
+            thresh = 1e-9 if it == drop_at else 10.0
+            before = [p.detach().clone() for p in model.parameters()]
             if graphed:
-                out, info = step()
+                out, info = step(thresh=thresh)
             else:
                 out = model()
                 model.backward(out["total_loss"])
-                info = model.update()
-            assert not info["skipped"]
+                info = model.update(thresh)
+            assert info["skipped"] == (it == drop_at) and info["grad_norm"] > 0
+            changed = any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
+            assert changed != (it == drop_at), it
             losses.append([float(out[k].detach()) for k in ("loss_traj", "loss_pos_state", "loss_vel_state")])
+        steps = {float(s["step"]) for s in model.optimizer.state.values()}
+        assert steps == {float(iters - 1)}, steps                        # the dropped iteration did not count
         return torch.tensor(losses), [p.detach().clone() for p in model.parameters()]
 
     l0, p0 = run(False)
-    l1, p1 = run(True)
-    assert torch.allclose(l0, l1, rtol=2e-3, atol=1e-7), (l0, l1)
-    for a, b in zip(p0, p1):
-        assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)
+    for capture_update in (True, False):
+        l1, p1 = run(True, capture_update)
+        assert torch.allclose(l0, l1, rtol=2e-3, atol=1e-7), (capture_update, l0, l1)
+        for a, b in zip(p0, p1):
+            assert torch.allclose(a, b, rtol=1e-3, atol=1e-5), capture_update
 
 
 @pytest.mark.parametrize("noise", [0.3, 0.03])

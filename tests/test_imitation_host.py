@@ -268,3 +268,96 @@ def test_median_gradient_clipping_matches_the_reference_queue():
             assert len(mine_q[n]) == len(ref_q[n]) and all(abs(x - float(y)) < 1e-5 * max(1.0, x) for x, y in zip(mine_q[n], ref_q[n]))
         if it in (15, 16, 30):
             assert info["a"][2] and not info["b"][2]
+
+
+def test_device_median_clipping_equals_the_host_queue():
+    """median_clip_device_ (tensor ops only, graph-capturable) == median_clip_ (host queue, itself checked against the
+    reference's loop above) on a gradient sequence with outliers and dropped iterations."""
+    from ppr_diffphys_b200.imitation import median_clip_, median_clip_device_
+    g = torch.Generator().manual_seed(1)
+    names = ["a", "b", "c"]
+    shapes = {"a": (7,), "b": (3, 4), "c": (1,)}
+    host_q = {}
+    Q, cnt = torch.zeros(3, 11), torch.zeros((), dtype=torch.long)
+    n_clipped = 0
+    for it in range(45):
+        grads = {n: torch.randn(shapes[n], generator=g) * (0.1 if n == "b" else 1.0) for n in names}
+        if it in (14, 15, 31):
+            grads["a"] = grads["a"] * 80.0
+        if it in (20, 31):
+            grads["c"] = grads["c"] * 1e3
+        dropped = it in (3, 17, 33)
+        host = {n: v.clone() for n, v in grads.items()}
+        if not dropped:                                           # update() does not clip / enqueue a dropped iteration
+            info = median_clip_(host.items(), host_q)
+            n_clipped += sum(v[2] for v in info.values())
+        dev = [grads[n].clone() for n in names]
+        norms, clipped = median_clip_device_(dev, Q, cnt, torch.tensor(dropped))
+        for n, d in zip(names, dev):
+            assert torch.allclose(d, host[n], rtol=1e-5, atol=1e-8), (it, n)
+        if not dropped:
+            assert [bool(c) for c in clipped] == [info[n][2] for n in names], it
+        else:
+            assert not clipped.any()
+        assert int(cnt) == len(host_q.get("a", []))
+        for i, n in enumerate(names):
+            assert torch.allclose(Q[i, :int(cnt)], torch.tensor(host_q.get(n, [])), rtol=1e-6, atol=0), (it, n)
+    assert n_clipped >= 4 and int(cnt) == 11
+
+
+def test_update_drops_rolls_back_in_place_and_steps_the_scheduler():
+    """ImitationModel.update (device part + host part) on a CPU stand-in: a finite small gradient is applied; a gradient
+    above the threshold or a NaN one leaves parameters, moments and step counts untouched; with a snapshot two rounds old
+    the model and optimizer state roll back IN PLACE (same storage); the scheduler steps every iteration."""
+    from ppr_diffphys_b200.imitation import ImitationModel
+
+    class Toy(torch.nn.Module):
+        update_device, finish_update = ImitationModel.update_device, ImitationModel.finish_update
+        update, save_checkpoint = ImitationModel.update, ImitationModel.save_checkpoint
+
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.ones(4))
+            self.v = torch.nn.Parameter(torch.ones(2, 2))
+            self.optimizer = torch.optim.AdamW([{"params": [self.w], "lr": 1e-2}, {"params": [self.v], "lr": 1e-3}],
+                                               weight_decay=1e-4, fused=True)
+            self.scheduler = torch.optim.lr_scheduler.OneCycleLR(self.optimizer, [1e-2, 1e-3], 20, pct_start=0.1,
+                                                                 cycle_momentum=False, anneal_strategy="linear")
+
+    def set_grads(m, scale):
+        m.w.grad = torch.full((4,), 0.1 * scale)
+        m.v.grad = torch.full((2, 2), -0.2 * scale)
+
+    m = Toy()
+    ptr = (m.w.data_ptr(), m.v.data_ptr())
+    set_grads(m, 1.0)
+    info = m.update(keep_grads=True)
+    assert not info["skipped"] and abs(info["grad_norm"] - (4 * 0.01 + 4 * 0.04) ** 0.5) < 1e-6
+    assert float(m.w[0]) < 1.0 and float(m.v[0, 0]) > 1.0 and m.scheduler.last_epoch == 1
+    mom_ptr = m.optimizer.state[m.w]["exp_avg"].data_ptr()
+    m.save_checkpoint()                                            # snapshot A (after one step)
+    w_a, step_a = m.w.detach().clone(), float(m.optimizer.state[m.w]["step"])
+    exp_a = m.optimizer.state[m.w]["exp_avg"].clone()
+    for bad in (1e4, float("nan")):                                # no two-rounds-old snapshot yet: drop only
+        before = (m.w.detach().clone(), m.optimizer.state[m.w]["exp_avg"].clone(), float(m.optimizer.state[m.w]["step"]))
+        set_grads(m, bad)
+        info = m.update()
+        assert info["skipped"] and m.w.grad is None
+        assert torch.equal(m.w, before[0]) and torch.equal(m.optimizer.state[m.w]["exp_avg"], before[1])
+        assert float(m.optimizer.state[m.w]["step"]) == before[2]
+    assert m.scheduler.last_epoch == 3
+    set_grads(m, 1.0)
+    assert not m.update()["skipped"]
+    m.save_checkpoint()                                            # snapshot B; A is now two rounds old
+    set_grads(m, 0.5)
+    m.update()
+    assert not torch.equal(m.w, w_a)
+    set_grads(m, 1e4)
+    info = m.update()                                              # dropped -> roll back to A, in place
+    assert info["skipped"]
+    assert torch.equal(m.w, w_a) and float(m.optimizer.state[m.w]["step"]) == step_a
+    assert torch.equal(m.optimizer.state[m.w]["exp_avg"], exp_a)
+    assert (m.w.data_ptr(), m.v.data_ptr()) == ptr and m.optimizer.state[m.w]["exp_avg"].data_ptr() == mom_ptr
+    assert m.scheduler.last_epoch == 2                             # A's epoch (1) + this iteration's scheduler step
+    set_grads(m, 1.0)
+    assert not m.update()["skipped"] and not torch.equal(m.w, w_a)

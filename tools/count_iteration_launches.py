@@ -34,3 +34,10 @@ tot = sum(fam.values())
 print("kernel launches in one eager iteration: %d, GPU-busy %.3f ms" % (tot, sum(tim.values()) / 1e3))
 for k, v in fam.most_common():
     print("  %-36s %5d launches  %8.3f ms" % (k, v, tim[k] / 1e3))
+if "--names" in sys.argv:
+    byname = collections.Counter(); tn = collections.Counter()
+    for e in prof.events():
+        if e.device_type is not None and str(e.device_type).endswith("CUDA") and e.device_time_total >= 0:
+            byname[e.name[:150]] += 1; tn[e.name[:150]] += e.device_time_total
+    for k, v in byname.most_common():
+        print("  %3d x %7.1f us  %s" % (v, tn[k] / v, k))
