@@ -84,6 +84,14 @@ int ppr_model_set_checkpoint_every(ppr_model_t m, int32_t every);
  * (about two warps per scheduler of a B200, the measured break-even); 0 disables.  Same rule as the checkpoint policy: set before workspace_bytes. */
 int ppr_model_set_latency_envs(ppr_model_t m, int64_t max_envs);
 int64_t ppr_model_latency_envs(ppr_model_t m);
+/* Rollouts of at most `max_envs` environments (and within the latency rule above, checkpoint policy 1) use the TEAM
+ * layout: one environment per thread block of three warps -- the main warp runs the substep, two helper warps evaluate
+ * the ground contacts (eval_body_contacts, integrator_euler.py:93-179; half of a substep's instructions) of their share
+ * of the bodies concurrently on the other schedulers of the SM.  1.6-1.9x lower substep latency than one warp per
+ * environment on the reference's own shapes.  Default 296 (two blocks per SM of a B200); 0 disables.  Set before
+ * workspace_bytes. */
+int ppr_model_set_team_envs(ppr_model_t m, int64_t max_envs);
+int64_t ppr_model_team_envs(ppr_model_t m);
 /* introspection of the THROUGHPUT packing chosen for this articulation: a group is a warp (32 threads) or a
  * thread block (96 / 160 threads); each group hosts floor(threads / nb) environments, one thread per body. */
 int ppr_model_envs_per_group(ppr_model_t m);

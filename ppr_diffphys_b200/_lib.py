@@ -16,7 +16,7 @@ _vp, _i64, _f32 = C.c_void_p, C.c_int64, C.c_float
 EXPORTS = [
     "ppr_version", "ppr_model_create", "ppr_model_destroy", "ppr_model_set_joint_X_p", "ppr_model_set_joint_X_p_env", "ppr_model_set_attach",
     "ppr_model_set_gravity", "ppr_model_set_ground", "ppr_model_set_checkpoint_every", "ppr_model_set_latency_envs",
-    "ppr_model_latency_envs", "ppr_model_envs_per_group", "ppr_model_group_threads", "ppr_fk_forward", "ppr_fk_backward",
+    "ppr_model_latency_envs", "ppr_model_set_team_envs", "ppr_model_team_envs", "ppr_model_envs_per_group", "ppr_model_group_threads", "ppr_fk_forward", "ppr_fk_backward",
     "ppr_rollout_workspace_bytes", "ppr_rollout_forward", "ppr_rollout_backward", "ppr_se3_loss_forward",
     "ppr_se3_loss_backward", "ppr_frame_compose_forward", "ppr_frame_compose_backward", "ppr_launch_count",
     "ppr_rollout_shared_grad_floats", "ppr_rollout_reduce_scratch_bytes", "ppr_rollout_backward_shared",
@@ -46,6 +46,9 @@ def _declare(lib):
     lib.ppr_model_set_latency_envs.argtypes = [_vp, _i64]
     lib.ppr_model_latency_envs.argtypes = [_vp]
     lib.ppr_model_latency_envs.restype = _i64
+    lib.ppr_model_set_team_envs.argtypes = [_vp, _i64]
+    lib.ppr_model_team_envs.argtypes = [_vp]
+    lib.ppr_model_team_envs.restype = _i64
     lib.ppr_model_envs_per_group.argtypes = [_vp]
     lib.ppr_model_group_threads.argtypes = [_vp]
     lib.ppr_fk_forward.argtypes = [_vp, _i64] + [_vp] * 5

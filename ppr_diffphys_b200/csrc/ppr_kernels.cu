@@ -6,7 +6,7 @@
 // slots = position * envs + env, tree exchange through float4 areas of shared memory with one split-phase mbarrier and
 // one hardware barrier per substep) -- whichever wastes fewer lanes: human has 19 bodies, i.e. 59 % lane use per warp
 // but 99 % with 5 envs in a 96-thread block. The two are the `Comm` policy of the kernels below; batches too small
-// to fill the GPU run one env per warp (latency layout, rollout_geometry).
+// to fill the GPU run one env per warp (latency layout) or one per block with helper warps (TeamComm; rollout_geometry).
 // The body state (13 floats) lives in registers for the whole rollout; parent/child exchange of states and
 // wrenches follows the static articulation tree with ordered reads (no atomics -> deterministic, unlike the
 // reference's atomic_add/sub at integrator_euler.py:179,449,451).  The time loop is inside the kernel: one launch
@@ -99,13 +99,16 @@ struct ppr_model {
     int variant;              // 0: FREE+REVOLUTE, 1: FREE+COMPOUND (both: no limits, identity q_off), 2: generic
     int ckpt_every;           // checkpoint policy K (1 = every substep, the fast default)
     int64_t latency_envs;     // batches up to this many envs run one env per warp (latency layout)
+    int64_t team_envs;        // batches up to this many envs run one env per BLOCK of 1 + PPR_TEAM_H warps (team layout)
     int comm;                 // env packing of the rollout kernels: 0 per warp (128-thread blocks), 1 per 96-thread
                               // block, 2 per 160-thread block
 };
+#define PPR_TEAM_H 2          // helper warps of the team layout (see TeamComm)
+#define PPR_COMM_TEAM 3
 #ifndef PPR_NT1
 #define PPR_NT1 96
 #endif
-static const int kCommThreads[3] = {128, PPR_NT1, 160};
+static const int kCommThreads[4] = {128, PPR_NT1, 160, 32 * (1 + PPR_TEAM_H)};
 #define PPR_MAGIC 0x50505231u
 #define PPR_MAX_DEVICES 64
 // The model's arrays live on the device that was current at ppr_model_create; every entry point that launches runs on
@@ -235,6 +238,7 @@ template <int RQ, bool BULK> struct RowStream {
 template <int NT, bool ADJ = true> struct WarpComm {
     static constexpr int kThreads = NT;
     static constexpr bool kBlock = false;
+    static constexpr int kHelpers = 0;
     static constexpr int kExFloats = 0;
     __device__ __forceinline__ explicit WarpComm(float*) {}
     static __device__ __forceinline__ int64_t group() { return ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; }
@@ -279,6 +283,110 @@ template <int NT, bool ADJ = true> struct WarpComm {
     }
 };
 
+// Team layout (batches of a few hundred environments at most, where the GPU is mostly idle and only the LATENCY of a
+// substep counts): one environment per BLOCK of 1 + H warps.  Warp 0 (the main warp) runs the substep exactly like the
+// warp layout (tree exchange by shuffles) except for the ground contacts, which are half of its instruction stream
+// (profiles/README.md): those are evaluated concurrently by the H helper warps, each for its share of the bodies, on the
+// other schedulers of the SM.  Hand-off through shared memory and two named hardware barriers per substep:
+//   barrier 1  request published (main arrives and goes on with the joints; helpers wait)
+//   barrier 2  replies published (helpers arrive; main waits when it needs the contact wrench / adjoint)
+// A helper can only pass barrier 1 of substep t+1 after the main warp consumed the replies of t, and the main warp only
+// re-writes the request after the helpers arrived at barrier 2 of t (i.e. finished reading it): no double buffering.
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+template <int H, bool ADJ = true> struct TeamComm : WarpComm<32 * (1 + H), ADJ> {
+    static constexpr int kThreads = 32 * (1 + H);
+    static constexpr int kHelpers = H;
+    // forward: request = body state + world COM (4 quads), reply = contact wrench + active-contact record (3 quads)
+    // adjoint: request = wrench adjoint (2 quads), reply = body adjoint 13 + dL/dR 9 + world-COM adjoint 3 (7 quads)
+    static constexpr int kReqQuads = ADJ ? 2 : 4, kRepQuads = ADJ ? 7 : 3;
+    static constexpr int kExFloats = (kReqQuads + H * kRepQuads) * 4 * 32;
+    float4* req;   // [kReqQuads][32]
+    float4* rep;   // [H][kRepQuads][32]
+    int helper;    // helper warp (0..H-1) that owns this lane's body
+    __device__ __forceinline__ explicit TeamComm(float* sm)
+        : WarpComm<32 * (1 + H), ADJ>(sm), req((float4*)sm), rep((float4*)sm + kReqQuads * 32), helper(0) {}
+    static __device__ __forceinline__ int64_t group() { return blockIdx.x; }
+    static __device__ __forceinline__ int role() { return threadIdx.x >> 5; }   // 0: main warp, 1..H: helper warps
+    // bodies with contact points are dealt round-robin to the helpers (quadruped feet / biped feet split evenly)
+    __device__ __forceinline__ void assign(bool has_points) {
+        const unsigned m = __ballot_sync(FULL, has_points);
+        helper = __popc(m & ((1u << (threadIdx.x & 31)) - 1u)) % H;
+    }
+    __device__ __forceinline__ bool mine() const { return helper == role() - 1; }
+    // ---- forward
+    __device__ __forceinline__ void request_contacts(const BodyF& s, F3 xc) {
+        const int l = threadIdx.x & 31;
+        req[0 * 32 + l] = make_float4(s.x.x, s.x.y, s.x.z, s.r.x);
+        req[1 * 32 + l] = make_float4(s.r.y, s.r.z, s.r.w, s.w.x);
+        req[2 * 32 + l] = make_float4(s.w.y, s.w.z, s.v.x, s.v.y);
+        req[3 * 32 + l] = make_float4(s.v.z, xc.x, xc.y, xc.z);
+        named_bar_arrive(1, kThreads);
+    }
+    __device__ __forceinline__ void await_request(BodyF& s, F3& xc) {
+        named_bar_sync(1, kThreads);
+        const int l = threadIdx.x & 31;
+        const float4 u0 = req[0 * 32 + l], u1 = req[1 * 32 + l], u2 = req[2 * 32 + l], u3 = req[3 * 32 + l];
+        s.x = v3<float>(u0.x, u0.y, u0.z); s.r = q4<float>(u0.w, u1.x, u1.y, u1.z);
+        s.w = v3<float>(u1.w, u2.x, u2.y); s.v = v3<float>(u2.z, u2.w, u3.x);
+        xc = v3<float>(u3.y, u3.z, u3.w);
+    }
+    __device__ __forceinline__ void reply_contacts(const WrenchF& F, unsigned long long rlo, unsigned long long rhi) {
+        float4* r = rep + (role() - 1) * kRepQuads * 32 + (threadIdx.x & 31);
+        r[0 * 32] = make_float4(F.t.x, F.t.y, F.t.z, F.f.x);
+        r[1 * 32] = make_float4(F.f.y, F.f.z, __uint_as_float((unsigned)rlo), __uint_as_float((unsigned)(rlo >> 32)));
+        r[2 * 32] = make_float4(__uint_as_float((unsigned)rhi), __uint_as_float((unsigned)(rhi >> 32)), 0.f, 0.f);
+        named_bar_arrive(2, kThreads);
+    }
+    __device__ __forceinline__ void await_contacts(WrenchF& F, unsigned long long& rlo, unsigned long long& rhi) {
+        named_bar_sync(2, kThreads);
+        const float4* r = rep + helper * kRepQuads * 32 + (threadIdx.x & 31);
+        const float4 a = r[0 * 32], b = r[1 * 32], c = r[2 * 32];
+        F.t = v3<float>(a.x, a.y, a.z); F.f = v3<float>(a.w, b.x, b.y);
+        rlo = (unsigned long long)__float_as_uint(b.z) | ((unsigned long long)__float_as_uint(b.w) << 32);
+        rhi = (unsigned long long)__float_as_uint(c.x) | ((unsigned long long)__float_as_uint(c.y) << 32);
+    }
+    // ---- adjoint
+    __device__ __forceinline__ void request_contacts_adj(const WrenchF& w) {
+        const int l = threadIdx.x & 31;
+        req[0 * 32 + l] = make_float4(w.t.x, w.t.y, w.t.z, w.f.x);
+        req[1 * 32 + l] = make_float4(w.f.y, w.f.z, 0.f, 0.f);
+        named_bar_arrive(1, kThreads);
+    }
+    __device__ __forceinline__ void await_request_adj(WrenchF& w) {
+        named_bar_sync(1, kThreads);
+        const int l = threadIdx.x & 31;
+        const float4 a = req[0 * 32 + l], b = req[1 * 32 + l];
+        w.t = v3<float>(a.x, a.y, a.z); w.f = v3<float>(a.w, b.x, b.y);
+    }
+    __device__ __forceinline__ void reply_contacts_adj(const BodyF& a, const M3F& G, F3 axc) {
+        float4* r = rep + (role() - 1) * kRepQuads * 32 + (threadIdx.x & 31);
+        r[0 * 32] = make_float4(a.x.x, a.x.y, a.x.z, a.r.x);
+        r[1 * 32] = make_float4(a.r.y, a.r.z, a.r.w, a.w.x);
+        r[2 * 32] = make_float4(a.w.y, a.w.z, a.v.x, a.v.y);
+        r[3 * 32] = make_float4(a.v.z, axc.x, axc.y, axc.z);
+        r[4 * 32] = make_float4(G.m[0], G.m[1], G.m[2], G.m[3]);
+        r[5 * 32] = make_float4(G.m[4], G.m[5], G.m[6], G.m[7]);
+        r[6 * 32] = make_float4(G.m[8], 0.f, 0.f, 0.f);
+        named_bar_arrive(2, kThreads);
+    }
+    __device__ __forceinline__ void await_contacts_adj(BodyF& a, M3F& G, F3& axc) {
+        named_bar_sync(2, kThreads);
+        const float4* r = rep + helper * kRepQuads * 32 + (threadIdx.x & 31);
+        const float4 u0 = r[0 * 32], u1 = r[1 * 32], u2 = r[2 * 32], u3 = r[3 * 32], u4 = r[4 * 32], u5 = r[5 * 32],
+                     u6 = r[6 * 32];
+        a.x += v3<float>(u0.x, u0.y, u0.z); a.r += q4<float>(u0.w, u1.x, u1.y, u1.z);
+        a.w += v3<float>(u1.w, u2.x, u2.y); a.v += v3<float>(u2.z, u2.w, u3.x);
+        axc += v3<float>(u3.y, u3.z, u3.w);
+        G.m[0] += u4.x; G.m[1] += u4.y; G.m[2] += u4.z; G.m[3] += u4.w;
+        G.m[4] += u5.x; G.m[5] += u5.y; G.m[6] += u5.z; G.m[7] += u5.w; G.m[8] += u6.x;
+    }
+};
+
 // Block-wide variant: values are published in shared memory ([component][thread], conflict-free), one
 // __syncthreads, then read at the partner's slot. In the substep loops a parent_state* call always alternates with
 // a gather_* call (different areas `ex` / `msg`), which makes the single barrier per call sufficient: every read of
@@ -287,6 +395,7 @@ template <int NT, bool ADJ = true> struct WarpComm {
 template <int NT, bool ADJ = true> struct BlockComm {
     static constexpr int kThreads = NT;
     static constexpr bool kBlock = true;
+    static constexpr int kHelpers = 0;
     // exchange areas are arrays of float4 [k][NT] (thread t's k-th quad at [k * NT + t]): one LDS.128 / STS.128 moves
     // what four scalar accesses did, conflict-free because consecutive threads touch consecutive 16-byte slots.
     // The forward kernel exchanges less (state down, wrench up) than the adjoint (state + wrench adjoint down, body
@@ -596,14 +705,14 @@ __device__ __forceinline__ float support_lower_bound(const float* __restrict__ T
 template <bool SUP>   // SUP: apply the support-function cull (forward pass; the adjoint's rare overflow path skips it)
 __device__ __forceinline__ int contact_candidates(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
                                                   const volatile float* st, int* __restrict__ clist, float& m0,
-                                                  float& m1, float& m2) {
+                                                  float& m1, float& m2, bool todo = true) {
     float w = s.r.w, ux = s.r.x, uy = s.r.y, uz = s.r.z;
     m0 = 2.f * (w * uz + uy * ux); m1 = 2.f * w * w - 1.f + 2.f * uy * uy; m2 = 2.f * (uy * uz - w * ux);
     const int b = L.body;
     float ylow = s.x.y + fminf(m0 * st[(ST_AABB + 0) * 32 + b], m0 * st[(ST_AABB + 3) * 32 + b]) +
                  fminf(m1 * st[(ST_AABB + 1) * 32 + b], m1 * st[(ST_AABB + 4) * 32 + b]) +
                  fminf(m2 * st[(ST_AABB + 2) * 32 + b], m2 * st[(ST_AABB + 5) * 32 + b]) - st[(ST_AABB + 6) * 32 + b];
-    bool maybe = L.valid && M.ground && (L.c1 > L.c0) && !(ylow > 1e-6f);
+    bool maybe = L.valid && M.ground && (L.c1 > L.c0) && !(ylow > 1e-6f) && todo;   // todo: team layout, see TeamComm
     bool big = (L.c1 - L.c0) > M.big_threshold;
 #ifndef PPR_NO_SUPPORT_CULL
     if (SUP && maybe && big) {   // (every big body has a table; the index is fetched here so that it costs no register)
@@ -707,9 +816,10 @@ template <int RQ> __device__ __forceinline__ void row_load(const float4* r, Body
 //   warp_contacts_search: which points penetrate (needs only this warp's body states)  -> cand / pen
 //   warp_contacts_eval  : subtracts their contact wrenches from F (per lane = per body) and records the active ones
 __device__ __forceinline__ int warp_contacts_search(const DevModel& M, const LaneInfo& L, int lane, const BodyF& s,
-                                                    const volatile float* st, int* __restrict__ clist, unsigned& pen) {
+                                                    const volatile float* st, int* __restrict__ clist, unsigned& pen,
+                                                    bool todo = true) {
     float m0, m1, m2;
-    int cand = contact_candidates<true>(M, L, lane, s, st, clist, m0, m1, m2);
+    int cand = contact_candidates<true>(M, L, lane, s, st, clist, m0, m1, m2, todo);
     pen = 0;
     if (cand == -2) {
         // small body (<= big_threshold <= 32 points, e.g. 8 box corners): test all points with four loads in flight and
@@ -986,9 +1096,13 @@ __device__ __forceinline__ WrenchF forces_pre(Comm& comm, const DevModel& M, con
                                               const M3F& Rb, F3 xc, const JointCtl<float>& ctl, const ContactMat<float>& cm0,
                                               const volatile float* st, const float4* xpq, int* clist, const float* res_f_row,
                                               float* grf_row, WrenchF& F, WrenchF& G, ContactRec& rec, float* ang) {
-    comm.post_state(s, xc);   // published before the (warp-dependent) contact search, awaited after it
-    unsigned pen;
-    const int cand = warp_contacts_search(M, L, lane, s, st, clist, pen);
+    unsigned pen = 0;
+    int cand = 0;
+    if constexpr (Comm::kHelpers > 0) comm.request_contacts(s, xc);   // team layout: the helper warps evaluate the contacts
+    else {
+        comm.post_state(s, xc);   // published before the (warp-dependent) contact search, awaited after it
+        cand = warp_contacts_search(M, L, lane, s, st, clist, pen);
+    }
     // joints: this lane is the child of its joint
     BodyF P;
     F3 xcp;
@@ -1009,7 +1123,11 @@ __device__ __forceinline__ WrenchF forces_pre(Comm& comm, const DevModel& M, con
         F.t = v3<float>(res_f_row[0], res_f_row[1], res_f_row[2]);
         F.f = v3<float>(res_f_row[3], res_f_row[4], res_f_row[5]);
     }
-    warp_contacts_eval(M, L, lane, s, Rb, xc, cm0, cand, pen, clist, F, rec);
+    if constexpr (Comm::kHelpers > 0) {
+        WrenchF Fc;
+        comm.await_contacts(Fc, rec.lo, rec.hi);
+        F.t += Fc.t; F.f += Fc.f;
+    } else warp_contacts_eval(M, L, lane, s, Rb, xc, cm0, cand, pen, clist, F, rec);
     G = F;
     if (grf_row && L.valid) store_wrench_row(grf_row, F);
     if (L.type != JT_FREE) { F.t -= t + cross(ac, f); F.f -= f; }
@@ -1065,7 +1183,8 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     extern __shared__ __align__(16) float smem[];
     Comm comm(smem + SL::comm);
     const int64_t group = Comm::group();
-    const int64_t warp = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);  // global warp: owns checkpoint rows
+    // global warp: owns checkpoint rows (team layout: one row per block, written by its main warp)
+    const int64_t warp = Comm::kHelpers > 0 ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     int* clist = (int*)(smem + SL::clist) + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
     volatile float* st = smem + SL::st;
@@ -1076,6 +1195,7 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
     if (M.nc > 0) cm0 = load_mat(M, 0);
     LaneInfo L = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M), Comm::kBlock && PPR_BODY_MAJOR);
+    if constexpr (Comm::kHelpers > 0) comm.assign(L.valid && L.c1 > L.c0);
     // per-env parameters of this body / joint -> shared memory
     int64_t ebp = (int64_t)L.env * A.pstride * M.nb + L.body;
     par_store<NT>(par, A.inv_m[ebp], A.I + ebp * 9, A.inv_I + ebp * 9);
@@ -1101,6 +1221,27 @@ rollout_forward_kernel(DevModel M, RolloutArgs A) {
     }
     __syncthreads();  // the static table is per block (all warps stage identical values)
 
+    if constexpr (Comm::kHelpers > 0) {
+        if (Comm::role() > 0) {
+            // ---- helper warp of the team layout: the ground contacts of its share of the bodies, one reply per substep
+            // (same trip count as the main warp's loop below)
+            const int64_t nsub = (A.out_grf || A.out_jaf) ? A.nsteps : A.nsteps - 1;
+            const bool todo = comm.mine();
+            for (int64_t t = 0; t < nsub; ++t) {
+                BodyF hs;
+                F3 hxc;
+                comm.await_request(hs, hxc);
+                const M3F hR = qmat(hs.r);
+                unsigned pen;
+                const int cand = warp_contacts_search(M, L, lane, hs, st, clist, pen, todo);
+                WrenchF Fc = wrench_zero<float>();
+                ContactRec rec;
+                warp_contacts_eval(M, L, lane, hs, hR, hxc, cm0, cand, pen, clist, Fc, rec);
+                comm.reply_contacts(Fc, rec.lo, rec.hi);
+            }
+            return;
+        }
+    }
     constexpr int RQ = RowOf<JM>::kQuads;
     float4* ck = (float4*)A.ckpt + (warp * RQ) * 32 + lane;
     const int64_t ck_step = A.nwarps * RQ * 32;   // in float4
@@ -1159,7 +1300,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     extern __shared__ __align__(16) float smem[];
     Comm comm(smem + SL::comm);
     const int64_t group = Comm::group();
-    const int64_t warp = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    const int64_t warp = Comm::kHelpers > 0 ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     int* clist = (int*)(smem + SL::clist) + (threadIdx.x >> 5) * 32 * PPR_CLIST_STRIDE;
     volatile float* st = smem + SL::st;
@@ -1176,6 +1317,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
     ContactMat<float> cm0 = {0.f, 0.f, 0.f, 0.f};
     if (M.nc > 0) cm0 = load_mat(M, 0);
     LaneInfo L = lane_setup(M, group, Comm::slot(), A.bs, Comm::envs_per_group(M), Comm::kBlock && PPR_BODY_MAJOR);
+    if constexpr (Comm::kHelpers > 0) comm.assign(L.valid && L.c1 > L.c0);
     int64_t eb = (int64_t)L.env * M.nb + L.body;
     int64_t ebp = (int64_t)L.env * A.pstride * M.nb + L.body;
     par_store<NT>(par, A.inv_m[ebp], A.I + ebp * 9, A.inv_I + ebp * 9);
@@ -1218,6 +1360,35 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
 #endif
     RowStream<RQ, BULK> rows(roww, (unsigned long long*)(smem + SL::rowbar) + (threadIdx.x >> 5), lane);
 
+    if constexpr (Comm::kHelpers > 0 && !RECOMP) {
+        if (Comm::role() > 0) {
+            // ---- helper warp of the team layout: K3^T of its share of the bodies.  It streams the block's checkpoint
+            // rows itself (state + active-contact record), so that only the wrench adjoint has to come from the main warp.
+            const bool todo = comm.mine();
+            for (int64_t tp = last - 1; tp >= 0; --tp) {
+                if (!prefetched) rows.issue(ckw + tp * ck_step);
+                rows.wait();
+                BodyF hs;
+                WrenchF hF;
+                ContactRec rec;
+                float hang[3];
+                row_load<RQ>(row4, hs, hF, rec, hang);
+                prefetched = tp > 0;
+                if (prefetched) rows.issue(ckw + (tp - 1) * ck_step);
+                if (!todo) { rec.lo = 0ull; rec.hi = 0ull; }
+                const M3F hR = qmat(hs.r);
+                const F3 hxc = hs.x + mrot(hR, st_vec3(st, ST_COM, L.body));
+                WrenchF aF;
+                comm.await_request_adj(aF);
+                BodyF aS = body_zero<float>();
+                M3F hG = m3_zero<float>();
+                F3 axc = vzero<float>();
+                warp_contacts_adj(M, L, lane, hs, hR, hxc, cm0, st, clist, rec, aF, aS, hG, axc);
+                comm.reply_contacts_adj(aS, hG, axc);
+            }
+            return;
+        }
+    }
     BodyF adjN = body_zero<float>();
     // rows of the never-differentiated last substep (dp_model.py:397): zero gradient
     if (L.valid) {
@@ -1330,6 +1501,7 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
             q4.x += gc.z * gd.y; q4.y += gc.z * gd.z;
             acc[0 * NT] = q0; acc[1 * NT] = q1; acc[2 * NT] = q2; acc[3 * NT] = q3; acc[4 * NT] = q4;
         }
+        if constexpr (Comm::kHelpers > 0) comm.request_contacts_adj(adjF);   // team layout: helpers replay the contacts
         comm.post_state_w(s, xc, adjF);   // published before the contact replay, awaited after it
 #ifdef PPR_CONTACTS_EARLY
         // K3^T (needs only this body's adjF)
@@ -1372,7 +1544,8 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
 #ifndef PPR_CONTACTS_EARLY
         // K3^T (needs only this body's adjF and feeds only this body's adjoint): after the parent adjoint is published,
         // so that the parent is not held up by the replay of this body's contact points
-        warp_contacts_adj(M, L, lane, s, Rb, xc, cm0, st, clist, rec, adjF, adjS, G, adj_xc);
+        if constexpr (Comm::kHelpers > 0) comm.await_contacts_adj(adjS, G, adj_xc);
+        else warp_contacts_adj(M, L, lane, s, Rb, xc, cm0, st, clist, rec, adjF, adjS, G, adj_xc);
 #endif
         // world COM -> pose: own-body part of the pose adjoint, evaluated while the children publish theirs
         adjS.x += adj_xc;
@@ -1410,7 +1583,9 @@ rollout_backward_kernel(DevModel M, RolloutArgs A) {
         const int P = 2 * M.nqd + 19 * M.nb;
         float* out = A.adj_partial + (int64_t)blockIdx.x * P;
         // (warp layout: the warps of a partially filled last block that own no environment have left the kernel)
-        const int nalive = Comm::kBlock ? NT : (int)min((int64_t)NT, (A.ngroups - (int64_t)blockIdx.x * (NT / 32)) * 32);
+        // (team layout: the helper warps have left as well, the main warp reduces alone)
+        const int nalive = Comm::kHelpers > 0 ? 32 : Comm::kBlock ? NT
+                         : (int)min((int64_t)NT, (A.ngroups - (int64_t)blockIdx.x * (NT / 32)) * 32);
         for (int i = threadIdx.x; i < M.nb * 25; i += nalive) {
             const int b = i / 25, c = i - b * 25;
             float sum = 0.f;
@@ -1688,6 +1863,8 @@ extern "C" int ppr_model_create(const ppr_model_desc* D, ppr_model_t* out) {
     m->ckpt_every = 1;
     m->latency_envs = 1024;   // ~148 SMs x 4 schedulers x 2 warps: measured break-even of the two layouts on B200
     if (const char* e = getenv("PPR_LATENCY_ENVS")) m->latency_envs = atoll(e);
+    m->team_envs = 296;       // 2 blocks of 3 warps per SM: every warp still (nearly) has a scheduler to itself
+    if (const char* e = getenv("PPR_TEAM_ENVS")) m->team_envs = atoll(e);
     m->xpj_offset = o_xpj;
     m->h_xpj.assign(D->joint_X_p, D->joint_X_p + nb * 7);
     m->magic = PPR_MAGIC;
@@ -1747,6 +1924,13 @@ extern "C" int ppr_model_set_latency_envs(ppr_model_t m, int64_t max_envs) {
     return 0;
 }
 extern "C" int64_t ppr_model_latency_envs(ppr_model_t m) { return check(m) ? m->latency_envs : PPR_E_HANDLE; }
+extern "C" int ppr_model_set_team_envs(ppr_model_t m, int64_t max_envs) {
+    if (!check(m)) return PPR_E_HANDLE;
+    if (max_envs < 0) return PPR_E_ARG;
+    m->team_envs = max_envs;
+    return 0;
+}
+extern "C" int64_t ppr_model_team_envs(ppr_model_t m) { return check(m) ? m->team_envs : PPR_E_HANDLE; }
 extern "C" int ppr_model_envs_per_group(ppr_model_t m) {
     if (!check(m)) return PPR_E_HANDLE;
     return m->comm == 0 ? m->d.epw : kCommThreads[m->comm] / m->d.nb;
@@ -1769,6 +1953,12 @@ static inline void rollout_geometry(const ppr_model* m, int64_t bs, int64_t& ngr
     comm = m->comm;
     epw = m->d.epw;
     if (bs <= m->latency_envs) { comm = 0; epw = 1; }
+    // still smaller batches: the contacts of an environment move to helper warps (team layout; stored rows only)
+    if (comm == 0 && epw == 1 && bs <= m->team_envs && m->ckpt_every == 1) {
+        comm = PPR_COMM_TEAM;
+        ngroups = bs; nwarps = bs; grid = (unsigned)bs;
+        return;
+    }
     const int nt = kCommThreads[comm];
     if (comm == 0) {
         ngroups = (bs + epw - 1) / epw;
@@ -1835,6 +2025,11 @@ template <class K> static cudaError_t launch_rollout(K kernel, size_t smem, unsi
             if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, d_, A); \
             else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, d_, A); \
             else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, 128, st, d_, A); \
+        } else if (comm_ == PPR_COMM_TEAM) {                                                                         \
+            typedef TeamComm<PPR_TEAM_H, ADJ> C_;                                                                    \
+            if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, C_::kThreads, st, d_, A); \
+            else if (m->variant == 1) e_ = launch_rollout(KERNEL<C_, JM_COMPOUND, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, C_::kThreads, st, d_, A); \
+            else e_ = launch_rollout(KERNEL<C_, JM_ALL, true, true __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, C_::kThreads, st, d_, A); \
         } else if (comm_ == 1) {                                                                                     \
             typedef BlockComm<PPR_NT1, ADJ> C_;                                                                        \
             if (m->variant == 0) e_ = launch_rollout(KERNEL<C_, JM_REVOLUTE, false, false __VA_ARGS__>, SmemLayout<C_, ADJ>::bytes, grid, PPR_NT1, st, d_, A); \

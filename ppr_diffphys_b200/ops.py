@@ -109,7 +109,7 @@ class SimEnv:
     def _snapshot(self):
         """Everything of the mutable model state that a rollout's forward and backward must agree on."""
         xp = self._joint_X_p
-        return (self.checkpoint_every, self.latency_envs, self.joint_attach_ke, self.joint_attach_kd, self._gravity,
+        return (self.checkpoint_every, self.latency_envs, self.team_envs, self.joint_attach_ke, self.joint_attach_kd, self._gravity,
                 self._ground, xp.data_ptr() if xp.is_cuda else None, tuple(xp.shape), xp._version)
 
     @property
@@ -176,6 +176,15 @@ class SimEnv:
     @property
     def latency_envs(self):
         return int(self._lib.ppr_model_latency_envs(self._h))
+
+    def set_team_envs(self, max_envs):
+        """Batches of at most ``max_envs`` environments run one environment per block of three warps, the ground contacts
+        on two helper warps (team layout: lowest substep latency for a few hundred environments at most)."""
+        _lib.check(self._lib.ppr_model_set_team_envs(self._h, int(max_envs)), "ppr_model_set_team_envs")
+
+    @property
+    def team_envs(self):
+        return int(self._lib.ppr_model_team_envs(self._h))
 
     @property
     def packing(self):

@@ -388,7 +388,8 @@ def test_checkpoint_every_k_recompute(robot, every):
 
 @pytest.mark.parametrize("robot", ["laikago", "human", "quad", "mixed"])
 def test_latency_layout_equals_throughput_layout(robot):
-    """Small batches run one environment per warp (ppr_model_set_latency_envs), large ones the block / warp packing
+    """Small batches run one environment per warp (ppr_model_set_latency_envs) or, smaller still, one per block of three
+    warps with the ground contacts on two helper warps (ppr_model_set_team_envs); large ones the block / warp packing
     chosen for throughput: same arithmetic per body, so trajectories, force side channels and gradients agree to
     rounding."""
     from ppr_diffphys_b200 import SimEnv
@@ -403,9 +404,10 @@ def test_latency_layout_equals_throughput_layout(robot):
         d = settle_height(rm, d, 0.002)
     dev = torch.device("cuda:0")
     out = []
-    for lat in (0, 1 << 20):
+    for lat, team in ((0, 0), (1 << 20, 0), (1 << 20, 1 << 20)):
         env = SimEnv(rm)
         env.set_latency_envs(lat)
+        env.set_team_envs(team)
         a, _, _ = flat_args(d, dev)
         pos, vel, caller = run_cuda(env, a, bs, T, stride)
         ((pos ** 2).sum() + (vel ** 2).sum() * 0.01).backward()
@@ -413,13 +415,14 @@ def test_latency_layout_equals_throughput_layout(robot):
                     [a[k].grad for k in KEYS]))
     # the kernel instances of the two layouts are separate compilations (different fma contraction): last-bit level
     # (joint forces amplify a last-bit pose difference by the 8e3..1.6e4 N/m attachment stiffness)
-    for name, tol, x, y in zip(("pos", "vel", "grf", "jaf"), (2e-6, 2e-6, 1e-4, 1e-4), out[0][:4], out[1][:4]):
-        assert rel(x, y.double().cpu()) < tol, (name, rel(x, y.double().cpu()))
-    # gradients: 1e-5, except laikago in stiff contact where last-bit differences between two compilations are amplified
-    # like every other rounding difference (fp32 noise floor of that fixture: 1e-3 .. 5e-3, tests/test_oracle.py)
     gtol = 1e-4 if robot == "laikago" else 1e-5
-    for k, x, y in zip(KEYS, out[0][4], out[1][4]):
-        assert rel(x, y.double().cpu()) < gtol, (k, rel(x, y.double().cpu()))
+    for other, layout in ((out[1], "latency"), (out[2], "team")):
+        for name, tol, x, y in zip(("pos", "vel", "grf", "jaf"), (2e-6, 2e-6, 1e-4, 1e-4), out[0][:4], other[:4]):
+            assert rel(x, y.double().cpu()) < tol, (layout, name, rel(x, y.double().cpu()))
+        # gradients: 1e-5, except laikago in stiff contact where last-bit differences between two compilations are
+        # amplified like every other rounding difference (fp32 noise floor of that fixture: 1e-3 .. 5e-3, tests/test_oracle.py)
+        for k, x, y in zip(KEYS, out[0][4], other[4]):
+            assert rel(x, y.double().cpu()) < gtol, (layout, k, rel(x, y.double().cpu()))
 
 
 def test_single_frame_window_and_single_env():
@@ -460,6 +463,9 @@ def test_c_abi_error_codes(monkeypatch):
     env.set_latency_envs(0)
     assert lib.ppr_rollout_workspace_bytes(h, 2, 65) == -(-2 // epg) * (threads // 32) * 65 * rowf * 32 * 4
     assert lib.ppr_model_set_latency_envs(h, -1) == -1
+    assert env.team_envs == 296 and lib.ppr_model_set_team_envs(h, -1) == -1
+    env.set_team_envs(5)
+    assert env.team_envs == 5 and lib.ppr_model_team_envs(C.c_void_p(None)) == -3
     before = _lib.launch_count()
     env.fk(torch.zeros(3, env.nq, device="cuda"), torch.zeros(3, env.nqd, device="cuda"))
     assert _lib.launch_count() == before + 1

@@ -1,21 +1,25 @@
 """Small fwd+bwd rollouts of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck / initcheck):
-four robots x {throughput layout, latency layout, throughput layout + checkpoint-every-3 recompute + per-env
-joint_X_p}, plus the round-2 paths: shared (un-replicated) parameters with the epilogue reduction, the fused pose loss
-through the struct-argument entry points, and the refs-from-frames kernels.
-usage: compute-sanitizer --tool <tool> python tools/sanitize_smoke.py"""
+four robots x {throughput layout, latency layout, team layout, throughput layout + checkpoint-every-3 recompute +
+per-env joint_X_p}, plus the round-2 paths: shared (un-replicated) parameters with the epilogue reduction, the fused pose
+loss through the struct-argument entry points, and the refs-from-frames kernels.
+usage: compute-sanitizer --tool <tool> python tools/sanitize_smoke.py [mode substring, e.g. team]"""
 import sys, torch
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 from helpers import make_inputs, settle_height, make_mixed_robot
 from test_gpu_parity import flat_args, run_cuda
 from ppr_diffphys_b200 import ForwardWarp, ForwardWarpLoss, RefsFromFrames, SimEnv
+only = sys.argv[1] if len(sys.argv) > 1 else ''
 for robot in ['laikago', 'human', 'quad', make_mixed_robot()]:
     stride, F, bs = 4, 3, 9
     T = stride * (F - 1) + 1
     rm, d = make_inputs(robot, bs=bs, T=T, seed=3, res_f_std=0.05, torque_std=0.05)
     d = settle_height(rm, d, 0.003)
-    for mode in ('throughput', 'latency', 'recompute+per-env-X_p'):
+    for mode in ('throughput', 'latency', 'team', 'recompute+per-env-X_p'):
+        if only not in mode:
+            continue
         env = SimEnv(rm)
-        env.set_latency_envs(1 << 20 if mode == 'latency' else 0)
+        env.set_latency_envs(1 << 20 if mode in ('latency', 'team') else 0)
+        env.set_team_envs(1 << 20 if mode == 'team' else 0)
         if mode.startswith('recompute'):
             env.set_checkpoint_every(3)
             env.joint_X_p = torch.as_tensor(rm.joint_X_p).repeat(bs, 1).cuda()
@@ -38,9 +42,12 @@ for robot in ['laikago', 'human']:
     rm, d = make_inputs(robot, bs=bs, T=T, seed=3)
     d = settle_height(rm, d, 0.003)
     dev = torch.device('cuda:0')
-    for lat in (0, 1 << 20):
+    for lat, team in ((0, 0), (1 << 20, 0), (1 << 20, 1 << 20)):
+        if only and not (only == 'team' and team):
+            continue
         env = SimEnv(rm)
         env.set_latency_envs(lat)
+        env.set_team_envs(team)
         t = lambda x: torch.as_tensor(x, dtype=torch.float32, device=dev)
         m, nI = t(rm.body_mass), t(rm.norm_body_inertia)
         leaf = lambda x: x.clone().requires_grad_(True)
@@ -56,4 +63,4 @@ for robot in ['laikago', 'human']:
                                                  _Caller(env, bs, T, stride))
         loss.sum().backward()
         torch.cuda.synchronize()
-        print(rm.name, 'shared + fused loss + refs-from-frames', env.packing, 'lat', lat, 'ok', float(loss.sum()))
+        print(rm.name, 'shared + fused loss + refs-from-frames', env.packing, 'lat', lat, 'team', team, 'ok', float(loss.sum()))
