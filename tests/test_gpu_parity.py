@@ -237,6 +237,8 @@ def test_full_size_properties(robot, bs):
     d = settle_height(rm, d, 0.002)
     dev = torch.device("cuda:0")
     env = SimEnv(rm)
+    env.set_team_envs(0)   # the 7-env sub-batch must take the same layout as the full batch: bit-identity holds per kernel
+                           # instance (the team layout has its own test below)
 
     def run(dd, adj_scale=1.0, seed=1):
         a, n, _ = flat_args(dd, dev, drop=("torques", "res_f"))
@@ -268,6 +270,44 @@ def test_full_size_properties(robot, bs):
     _, _, g3, _, _ = run(d, adj_scale=2.0)
     for k in g1:
         assert torch.allclose(g3[k], 2 * g1[k], rtol=1e-5, atol=1e-6 * float(g1[k].abs().max())), k
+
+
+@pytest.mark.parametrize("robot", ["laikago", "human"])
+def test_team_layout_determinism_and_batch_independence(robot):
+    """Team layout (one env per block, contacts on helper warps): bit-exact determinism, and the first 7 of 40 envs computed
+    alone give bit-identical trajectories and gradients (an environment never sees its neighbours)."""
+    from ppr_diffphys_b200 import SimEnv
+    stride, F, bs = 16, 3, 40
+    T = stride * (F - 1) + 1
+    rm, d = make_inputs(robot, bs=bs, T=T, seed=2, lin_vel=0.3)
+    d = settle_height(rm, d, 0.002)
+    dev = torch.device("cuda:0")
+    env = SimEnv(rm)
+    env.set_latency_envs(1 << 20)
+    env.set_team_envs(1 << 20)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    nb = rm.nb
+    ap = torch.randn(F, bs, nb, 7, generator=g).to(dev)
+    av = (torch.randn(F, bs, nb, 6, generator=g) * 0.1).to(dev)
+
+    def run(dd, n):
+        a, _, _ = flat_args(dd, dev, drop=("torques", "res_f"))
+        pos, vel, caller = run_cuda(env, a, n, T, stride)
+        torch.autograd.backward([pos, vel], [ap[:, :n].reshape(F, -1, 7).contiguous(), av[:, :n].reshape(F, -1, 6).contiguous()])
+        return pos.detach(), vel.detach(), torch.stack(caller.grfs), {k: a[k].grad for k in KEYS if a.get(k) is not None}
+
+    p1, v1, f1, g1 = run(d, bs)
+    p2, v2, f2, g2 = run(d, bs)
+    assert torch.equal(p1, p2) and torch.equal(v1, v2) and torch.equal(f1, f2)
+    assert float(f1.abs().max()) > 0                       # the fixture is in contact: the helpers did something
+    for k in g1:
+        assert torch.isfinite(g1[k]).all() and torch.equal(g1[k], g2[k]), k
+    sub = {k: (v[:, :7] if k in ("torques", "res_f", "refs") else v[:7]) for k, v in d.items()}
+    ps, vs, fs, gs = run(sub, 7)
+    assert torch.equal(ps, p1.view(F, bs, nb, 7)[:, :7].reshape(F, -1, 7))
+    assert torch.equal(fs, f1.view(F, bs, nb, 6)[:, :7].reshape(F, -1, 6))
+    assert torch.equal(gs["q_init"], g1["q_init"].view(bs, -1)[:7].reshape(-1))
+    assert torch.equal(gs["refs"], g1["refs"].view(T, bs, -1)[:, :7].reshape(T, -1))
 
 
 def test_free_fall_full_size():
@@ -368,6 +408,7 @@ def test_checkpoint_every_k_recompute(robot, every):
     out = {}
     for K in (1, every):
         env = SimEnv(rm)
+        env.set_team_envs(0)   # K > 1 exists in the warp / block layouts only: compare within one kernel family (bit for bit)
         ws1 = env._lib.ppr_rollout_workspace_bytes(env._h, bs, T)
         env.set_checkpoint_every(K)
         ws = env._lib.ppr_rollout_workspace_bytes(env._h, bs, T)
